@@ -1,0 +1,103 @@
+/* bnp.h - C ABI of the B200-native batched BN254 pairing engine (libbnp.so).
+ *
+ * Drop-in boundary for the native path of qope/plonky2-bn254-pairing.  The reference has no FFI
+ * layer of its own: the boundary is its public Rust function set, and each entry point below is
+ * what a thin `extern "C"` crate binds for the function it names.
+ *
+ * Data layout (all entry points): structure-of-arrays by 64-bit limb, Montgomery form with
+ * R = 2^256, canonical (< p) - i.e. exactly ark-ff's `Fp.0.0: [u64; 4]`.  An array of n elements
+ * with K base-field values per element is   u64 buf[K][4][n]   (limb j of value k of element e at
+ * buf[(k*4 + j)*n + e]).
+ *     G1Affine : K = 2   (x, y)
+ *     G2Affine : K = 4   (x.c0, x.c1, y.c0, y.c1)
+ *     MyFq12   : K = 12  coeffs[0..11]; coeffs[i] + coeffs[i+6]*u is the Fq2 coefficient of w^i
+ * For k-way products the k points of one product sit side by side: G1 K = 2k, G2 K = 4k.
+ *
+ * Preconditions are the reference's: points are non-identity, on-curve, in the r-torsion subgroup;
+ * Fq12 inputs to the final exponentiation are non-zero (the reference panics on zero; this
+ * library returns zeros for that element).
+ *
+ * All functions return 0 on success or a negative BNP_E* code; nothing unwinds across the ABI.
+ * Host-pointer calls are synchronous.  `*_dev` calls take device pointers on the given device and
+ * only enqueue work on `stream` (a cudaStream_t passed as void*; NULL = the library's stream).
+ * There is no CPU fallback: without a CUDA device every compute call fails with BNP_ENODEV.
+ */
+#ifndef BNP_H
+#define BNP_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNP_OK 0
+#define BNP_EINVAL (-1)   /* bad argument */
+#define BNP_ENODEV (-2)   /* no usable CUDA device / not initialised */
+#define BNP_ECUDA (-3)    /* CUDA runtime error (see bnp_last_error) */
+#define BNP_ENOMEM (-4)
+#define BNP_EUNSUPPORTED (-5)
+
+#define BNP_VARIANT_REFERENCE 0 /* exponent (p^12-1)/r, bit-equal to final_exp_native.rs:209 */
+#define BNP_VARIANT_ARK 1       /* ark-ec 0.4.2 Bn254 final exponentiation (= variant 0 ^ 2x(6x^2+3x+1)) */
+
+/* Create per-device state (programs, constants, scratch, stream) on the listed CUDA devices;
+ * devices == NULL means device 0.  Idempotent. */
+int bnp_init(const int* devices, int n_devices);
+void bnp_shutdown(void);
+int bnp_device_count(void); /* devices initialised by bnp_init */
+const char* bnp_strerror(int code);
+const char* bnp_last_error(void); /* detail of the last BNP_ECUDA on this thread */
+
+/* miller_loop_native(Q, P) for n independent pairs  (miller_loop_native.rs:320). */
+int bnp_miller_loop_batch(const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n);
+/* multi_miller_loop_native(pairs) for n independent products of k pairs each, k in 1..4
+ * (miller_loop_native.rs:324). */
+int bnp_multi_miller_loop_batch(const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n, int k);
+/* final_exp_native(a)  (final_exp_native.rs:209). */
+int bnp_final_exp_batch(const uint64_t* in, uint64_t* out, size_t n, int variant);
+/* pairing(p, q) = final_exp_native(miller_loop_native(&q, &p))  (pairing.rs:20), one fused launch.
+ * Output in MyFq12 coefficient order; the Rust wrapper applies MyFq12 -> Fq12. */
+int bnp_pairing_batch(const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n, int variant);
+/* n independent k-way products  prod_j pairing(p_j, q_j), k in 1..4 (shared squarings, one final
+ * exponentiation per product): the Groth16-verify shape. */
+int bnp_multi_pairing_batch(const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n, int k, int variant);
+/* ONE product over all n pairs: out[12][4] = final_exp(prod_i miller(q_i, p_i)).  The pairs are split
+ * over the initialised devices; per-device partial products are combined on device 0. */
+int bnp_pairing_product(const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n, int variant);
+/* frobenius_map_native(a, power), any power (reduced mod 12)  (final_exp_native.rs:17). */
+int bnp_frobenius_batch(const uint64_t* in, uint64_t* out, size_t n, size_t power);
+/* MyFq12 `Mul`: out = a * b element-wise. */
+int bnp_fq12_mul_batch(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+
+/* ---- device-pointer variants (one device; no host<->device copies; asynchronous on `stream`) ---- */
+int bnp_miller_loop_dev(int device, void* stream, const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n, int k);
+/* Miller values up to a proper-subfield factor: only valid as input to a final exponentiation
+ * (what bnp_pairing_product reduces and gathers). */
+int bnp_miller_loop_fused_dev(int device, void* stream, const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n);
+int bnp_final_exp_dev(int device, void* stream, const uint64_t* in, uint64_t* out, size_t n, int variant);
+int bnp_pairing_dev(int device, void* stream, const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n, int k, int variant);
+int bnp_frobenius_dev(int device, void* stream, const uint64_t* in, uint64_t* out, size_t n, size_t power);
+int bnp_fq12_mul_dev(int device, void* stream, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+/* In-place tree product of n MyFq12 values (buf[12][4][n], destroyed) -> out[12][4][1]. */
+int bnp_fq12_product_dev(int device, void* stream, uint64_t* buf, uint64_t* out, size_t n);
+
+/* ---- introspection / measurement ---- */
+/* Algorithmic work of one element of the named program ("pairing_v0", "miller", "final_exp_v0", ...):
+ * 32x32->64 multiply-accumulates (64 per Fp product + 72 per Montgomery reduction), 0 if unknown. */
+uint64_t bnp_program_macs(const char* program);
+/* Kernel launches issued by this library since bnp_init (for bench.py's gpu_launches). */
+uint64_t bnp_launch_count(void);
+/* Dependency-free IMAD.WIDE.U32 throughput microbenchmark on `device`: writes multiply-accumulates
+ * per second (the roofline denominator) to *macs_per_s. */
+int bnp_imad_peak(int device, double* macs_per_s);
+/* Run an arbitrary sequencer program by name on device arrays (test hook for op-level parity). */
+int bnp_run_program_dev(int device, void* stream, const char* program, const uint64_t* g1, const uint64_t* g2,
+                        const uint64_t* f12, const uint64_t* aux, uint64_t* out, size_t n);
+/* Tuning knobs (0 keeps the default): threads per block (32/64/128) and shared-memory slots per thread. */
+int bnp_set_launch_config(int threads_per_block, int reserved);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNP_H */

@@ -1,0 +1,226 @@
+"""Host-side mirror of the reference's native-path interface, on top of the C ABI (include/bnp.h).
+
+Same names, argument order and meaning as the reference's public functions:
+
+    miller_loop_native(Q, P)              /root/reference/src/miller_loop_native.rs:320   (G2 first!)
+    multi_miller_loop_native(pairs)       /root/reference/src/miller_loop_native.rs:324   pairs = [(P, Q), ...]
+    final_exp_native(a)                   /root/reference/src/final_exp_native.rs:209
+    frobenius_map_native(a, power)        /root/reference/src/final_exp_native.rs:17
+    pairing(p, q)                         /root/reference/src/pairing.rs:20               (G1 first)
+
+plus the batched slice variants the north star adds (`*_batch`).  Values use the oracle's plain-integer
+conventions (Fq = int, Fq2 = (c0, c1), G1 = (x, y), G2 = (x, y) over Fq2, MyFq12 = 12 ints); this module
+converts to the ABI's Montgomery structure-of-arrays layout and back, nothing else - all arithmetic
+happens in libbnp.so on the GPU.  Errors surface as BnpError (the reference panics).
+"""
+import ctypes
+
+import numpy as np
+
+from . import native
+
+P = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
+MONT_R = (1 << 256) % P
+MONT_RINV = pow(MONT_R, P - 2, P)
+
+VARIANT_REFERENCE = 0
+VARIANT_ARK = 1
+
+
+# ----------------------------------------------------------------------------- marshalling
+def pack_soa(rows):
+    """rows: n sequences of K Fq ints -> uint64 array [K][4][n] of Montgomery limbs (ark's Fp.0.0)."""
+    n = len(rows)
+    K = len(rows[0]) if n else 0
+    buf = bytearray()
+    for r in rows:
+        assert len(r) == K
+        for v in r:
+            buf += (v * MONT_R % P).to_bytes(32, "little")
+    a = np.frombuffer(bytes(buf), dtype=np.uint64).reshape(n, K, 4)
+    return np.ascontiguousarray(a.transpose(1, 2, 0))
+
+
+def unpack_soa(arr):
+    """uint64 [K][4][n] Montgomery limbs -> n lists of K plain Fq ints (asserts canonical residues)."""
+    K, four, n = arr.shape
+    assert four == 4
+    a = np.ascontiguousarray(arr.transpose(2, 0, 1)).tobytes()
+    out = []
+    for e in range(n):
+        row = []
+        for k in range(K):
+            off = (e * K + k) * 32
+            m = int.from_bytes(a[off:off + 32], "little")
+            if m >= P:
+                raise native.BnpError("non-canonical residue returned by the device")
+            row.append(m * MONT_RINV % P)
+        out.append(row)
+    return out
+
+
+def g1_rows(points):
+    return [[p[0], p[1]] for p in points]
+
+
+def g2_rows(points):
+    return [[q[0][0], q[0][1], q[1][0], q[1][1]] for q in points]
+
+
+def _ptr(a):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+# ----------------------------------------------------------------------------- SoA-level calls (numpy in, numpy out)
+def miller_loop_soa(g1, g2, k=1):
+    lib = native.lib()
+    n = g1.shape[2]
+    out = np.empty((12, 4, n), dtype=np.uint64)
+    if k == 1:
+        native.check(lib.bnp_miller_loop_batch(_ptr(g1), _ptr(g2), _ptr(out), n))
+    else:
+        native.check(lib.bnp_multi_miller_loop_batch(_ptr(g1), _ptr(g2), _ptr(out), n, k))
+    return out
+
+
+def final_exp_soa(f, variant=VARIANT_REFERENCE):
+    lib = native.lib()
+    n = f.shape[2]
+    out = np.empty((12, 4, n), dtype=np.uint64)
+    native.check(lib.bnp_final_exp_batch(_ptr(f), _ptr(out), n, variant))
+    return out
+
+
+def pairing_soa(g1, g2, variant=VARIANT_REFERENCE, k=1):
+    lib = native.lib()
+    n = g1.shape[2]
+    out = np.empty((12, 4, n), dtype=np.uint64)
+    if k == 1:
+        native.check(lib.bnp_pairing_batch(_ptr(g1), _ptr(g2), _ptr(out), n, variant))
+    else:
+        native.check(lib.bnp_multi_pairing_batch(_ptr(g1), _ptr(g2), _ptr(out), n, k, variant))
+    return out
+
+
+def pairing_product_soa(g1, g2, variant=VARIANT_REFERENCE):
+    lib = native.lib()
+    n = g1.shape[2]
+    out = np.empty((12, 4, 1), dtype=np.uint64)
+    native.check(lib.bnp_pairing_product(_ptr(g1), _ptr(g2), _ptr(out), n, variant))
+    return out
+
+
+def frobenius_soa(f, power):
+    lib = native.lib()
+    n = f.shape[2]
+    out = np.empty((12, 4, n), dtype=np.uint64)
+    native.check(lib.bnp_frobenius_batch(_ptr(f), _ptr(out), n, power))
+    return out
+
+
+def fq12_mul_soa(a, b):
+    lib = native.lib()
+    n = a.shape[2]
+    out = np.empty((12, 4, n), dtype=np.uint64)
+    native.check(lib.bnp_fq12_mul_batch(_ptr(a), _ptr(b), _ptr(out), n))
+    return out
+
+
+# ----------------------------------------------------------------------------- batched slice variants (north star)
+def miller_loop_native_batch(Qs, Ps):
+    """[miller_loop_native(Q_i, P_i)]"""
+    if len(Qs) != len(Ps):
+        raise ValueError("length mismatch")
+    if not Qs:
+        return []
+    return unpack_soa(miller_loop_soa(pack_soa(g1_rows(Ps)), pack_soa(g2_rows(Qs))))
+
+
+def multi_miller_loop_native_batch(products):
+    """products: list of equal-length lists of (P, Q) tuples -> one MyFq12 per product (k <= 4)."""
+    if not products:
+        return []
+    k = len(products[0])
+    g1 = pack_soa([[c for (p, _) in prod for c in (p[0], p[1])] for prod in products])
+    g2 = pack_soa([[c for (_, q) in prod for c in (q[0][0], q[0][1], q[1][0], q[1][1])] for prod in products])
+    return unpack_soa(miller_loop_soa(g1, g2, k=k))
+
+
+def final_exp_native_batch(fs, variant=VARIANT_REFERENCE):
+    if not fs:
+        return []
+    return unpack_soa(final_exp_soa(pack_soa(fs), variant))
+
+
+def pairing_batch(Ps, Qs, variant=VARIANT_REFERENCE):
+    """[pairing(P_i, Q_i)] in MyFq12 coefficient order (see myfq12_to_ark for ark's nesting)."""
+    if len(Qs) != len(Ps):
+        raise ValueError("length mismatch")
+    if not Ps:
+        return []
+    return unpack_soa(pairing_soa(pack_soa(g1_rows(Ps)), pack_soa(g2_rows(Qs)), variant))
+
+
+def multi_pairing_batch(products, variant=VARIANT_REFERENCE):
+    """products: list of k-lists of (P, Q) -> prod_j pairing(P_j, Q_j) per product (Groth16-verify shape)."""
+    if not products:
+        return []
+    k = len(products[0])
+    g1 = pack_soa([[c for (p, _) in prod for c in (p[0], p[1])] for prod in products])
+    g2 = pack_soa([[c for (_, q) in prod for c in (q[0][0], q[0][1], q[1][0], q[1][1])] for prod in products])
+    return unpack_soa(pairing_soa(g1, g2, variant, k=k))
+
+
+def pairing_product(pairs, variant=VARIANT_REFERENCE):
+    """final_exp(prod_i miller(Q_i, P_i)) over ALL pairs (any count), split across the initialised GPUs."""
+    g1 = pack_soa(g1_rows([p for (p, _) in pairs]))
+    g2 = pack_soa(g2_rows([q for (_, q) in pairs]))
+    return unpack_soa(pairing_product_soa(g1, g2, variant))[0]
+
+
+def frobenius_map_native_batch(fs, power):
+    if not fs:
+        return []
+    return unpack_soa(frobenius_soa(pack_soa(fs), power))
+
+
+def fq12_mul_batch(As, Bs):
+    if not As:
+        return []
+    return unpack_soa(fq12_mul_soa(pack_soa(As), pack_soa(Bs)))
+
+
+# ----------------------------------------------------------------------------- the reference's scalar signatures (n = 1 calls)
+def miller_loop_native(Q, Pt):
+    return miller_loop_native_batch([Q], [Pt])[0]
+
+
+def multi_miller_loop_native(pairs):
+    if len(pairs) > 4:
+        # shared-squaring programs exist for k <= 4; larger products: product of single loops, which the
+        # reference's own test pins as equal (miller_loop_native.rs:336-348)
+        ms = miller_loop_native_batch([q for (_, q) in pairs], [p for (p, _) in pairs])
+        acc = ms[0]
+        for m in ms[1:]:
+            acc = fq12_mul_batch([acc], [m])[0]
+        return acc
+    return multi_miller_loop_native_batch([list(pairs)])[0]
+
+
+def final_exp_native(a):
+    return final_exp_native_batch([a])[0]
+
+
+def frobenius_map_native(a, power):
+    return frobenius_map_native_batch([a], power)[0]
+
+
+def pairing(p, q):
+    return pairing_batch([p], [q])[0]
+
+
+def myfq12_to_ark(a):
+    """`impl From<MyFq12> for Fq12`: MyFq12 coefficient order -> ark's [c0.c0, c0.c1, c0.c2, c1.c0, c1.c1, c1.c2]."""
+    c = [(a[i], a[i + 6]) for i in range(6)]
+    return [c[0], c[2], c[4], c[1], c[3], c[5]]

@@ -1,0 +1,499 @@
+// libbnp.so runtime: C ABI of include/bnp.h on top of the sequencer kernel (vm.cuh).
+// No torch types, no CPU fallback: every compute entry point fails with BNP_ENODEV without a device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/bnp.h"
+#include "microcode_tables.h"
+#include "vm.cuh"
+
+namespace {
+
+struct DevCtx {
+    int dev = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<u64*> d_prog;  // one device copy per program
+    uint4* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // staging for the host-pointer API
+    u64* stage[BNP_NARR] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t stage_bytes[BNP_NARR] = {0, 0, 0, 0, 0};
+};
+
+std::mutex g_mu;
+std::vector<DevCtx> g_ctx;
+std::atomic<uint64_t> g_launches{0};
+int g_threads_per_block = 64;
+thread_local std::string g_last_error;
+
+int cuda_fail(cudaError_t e, const char* what) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return BNP_ECUDA;
+}
+#define CK(call)                                      \
+    do {                                              \
+        cudaError_t _e = (call);                      \
+        if (_e != cudaSuccess) return cuda_fail(_e, #call); \
+    } while (0)
+
+const BnpProgram* find_program(const char* name, int* index = nullptr) {
+    for (uint32_t i = 0; i < BNP_NPROG; i++)
+        if (std::strcmp(BNP_PROGRAMS[i].name, name) == 0) {
+            if (index) *index = (int)i;
+            return &BNP_PROGRAMS[i];
+        }
+    return nullptr;
+}
+
+DevCtx* find_ctx(int device) {
+    for (auto& c : g_ctx)
+        if (c.dev == device) return &c;
+    return nullptr;
+}
+
+template <int T>
+int launch_T(DevCtx& c, const BnpProgram& p, int pidx, cudaStream_t st, u64* const arr[BNP_NARR], size_t n,
+             size_t stride) {
+    const size_t smem = (size_t)p.n_slots * 64 * T;
+    auto kern = bnp_vm_kernel<T>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
+    if (per_sm < 1) {
+        g_last_error = "program does not fit in shared memory";
+        return BNP_EUNSUPPORTED;
+    }
+    size_t blocks = (n + T - 1) / T;
+    blocks = std::min(blocks, (size_t)per_sm * c.sm_count);
+    const size_t total = blocks * T;
+    const size_t need = (size_t)std::max<uint32_t>(p.n_scratch, 1) * 64 * total;
+    if (need > c.scratch_bytes) {
+        CK(cudaStreamSynchronize(c.stream));
+        if (st != c.stream) CK(cudaStreamSynchronize(st));
+        if (c.scratch) CK(cudaFree(c.scratch));
+        c.scratch = nullptr;
+        c.scratch_bytes = 0;
+        CK(cudaMalloc(&c.scratch, need));
+        c.scratch_bytes = need;
+    }
+    VmArgs a;
+    a.prog = c.d_prog[pidx];
+    for (int i = 0; i < BNP_NARR; i++) a.arr[i] = arr[i];
+    a.scratch = c.scratch;
+    a.n = (u32)n;
+    a.stride = (u32)stride;
+    kern<<<(unsigned)blocks, T, smem, st>>>(a);
+    CK(cudaGetLastError());
+    g_launches++;
+    return BNP_OK;
+}
+
+// run one program over n elements on device arrays
+int launch(DevCtx& c, const char* prog, void* stream, const u64* g1, const u64* g2, const u64* f12, const u64* aux,
+           u64* out, size_t n, size_t stride = 0) {
+    if (n == 0) return BNP_OK;
+    if (n > 0x7fffffffull) return BNP_EINVAL;
+    int pidx = -1;
+    const BnpProgram* p = find_program(prog, &pidx);
+    if (!p) {
+        g_last_error = std::string("unknown program ") + prog;
+        return BNP_EUNSUPPORTED;
+    }
+    CK(cudaSetDevice(c.dev));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c.stream;
+    u64* arr[BNP_NARR] = {const_cast<u64*>(g1), const_cast<u64*>(g2), const_cast<u64*>(f12), out,
+                          const_cast<u64*>(aux)};
+    if (stride == 0) stride = n;
+    switch (g_threads_per_block) {
+        case 32: return launch_T<32>(c, *p, pidx, st, arr, n, stride);
+        case 128: return launch_T<128>(c, *p, pidx, st, arr, n, stride);
+        default: return launch_T<64>(c, *p, pidx, st, arr, n, stride);
+    }
+}
+
+int init_device(int dev) {
+    if (find_ctx(dev)) return BNP_OK;
+    CK(cudaSetDevice(dev));
+    DevCtx c;
+    c.dev = dev;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, dev));
+    c.sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    if (BNP_NCONST > BNP_MAX_CONST) return BNP_EUNSUPPORTED;
+    CK(cudaMemcpyToSymbol(BNP_CONSTS, BNP_CONST_TABLE, (size_t)BNP_NCONST * 64));
+    c.d_prog.resize(BNP_NPROG, nullptr);
+    for (uint32_t i = 0; i < BNP_NPROG; i++) {
+        const size_t bytes = (size_t)BNP_PROGRAMS[i].len * 8;
+        CK(cudaMalloc(&c.d_prog[i], bytes));
+        CK(cudaMemcpy(c.d_prog[i], BNP_PROGRAMS[i].code, bytes, cudaMemcpyHostToDevice));
+    }
+    g_ctx.push_back(c);
+    return BNP_OK;
+}
+
+int ensure_stage(DevCtx& c, int which, size_t bytes) {
+    if (bytes <= c.stage_bytes[which]) return BNP_OK;
+    if (c.stage[which]) CK(cudaFree(c.stage[which]));
+    c.stage[which] = nullptr;
+    c.stage_bytes[which] = 0;
+    CK(cudaMalloc(&c.stage[which], bytes));
+    c.stage_bytes[which] = bytes;
+    return BNP_OK;
+}
+
+// host [K][4][n] rows, elements [off, off+cnt)  <->  device [K][4][cnt]
+int copy_in(DevCtx& c, int which, const u64* host, size_t K, size_t n, size_t off, size_t cnt) {
+    int rc = ensure_stage(c, which, K * 32 * cnt);
+    if (rc) return rc;
+    CK(cudaMemcpy2DAsync(c.stage[which], cnt * 8, host + off, n * 8, cnt * 8, K * 4, cudaMemcpyHostToDevice, c.stream));
+    return BNP_OK;
+}
+
+int copy_out(DevCtx& c, int which, u64* host, size_t K, size_t n, size_t off, size_t cnt) {
+    CK(cudaMemcpy2DAsync(host + off, n * 8, c.stage[which], cnt * 8, cnt * 8, K * 4, cudaMemcpyDeviceToHost, c.stream));
+    return BNP_OK;
+}
+
+struct Split {
+    size_t off, cnt;
+};
+
+std::vector<Split> split_range(size_t n, size_t parts) {
+    std::vector<Split> s;
+    size_t off = 0;
+    for (size_t i = 0; i < parts; i++) {
+        size_t cnt = n / parts + (i < n % parts ? 1 : 0);
+        s.push_back({off, cnt});
+        off += cnt;
+    }
+    return s;
+}
+
+int sync_all() {
+    int rc = BNP_OK;
+    for (auto& c : g_ctx) {
+        if (cudaSetDevice(c.dev) != cudaSuccess) rc = BNP_ECUDA;
+        cudaError_t e = cudaStreamSynchronize(c.stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
+    }
+    return rc;
+}
+
+// generic host-pointer batch: inputs (which array id, K) -> program -> output K_out, sharded by index
+struct HostIn {
+    int which;
+    const u64* host;
+    size_t K;
+};
+
+int run_host(const char* prog, const std::vector<HostIn>& ins, u64* out, size_t K_out, size_t n) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ctx.empty()) return BNP_ENODEV;
+    if (n == 0) return BNP_OK;
+    for (auto& in : ins)
+        if (!in.host) return BNP_EINVAL;
+    if (!out) return BNP_EINVAL;
+    auto parts = split_range(n, g_ctx.size());
+    for (size_t d = 0; d < g_ctx.size(); d++) {
+        if (parts[d].cnt == 0) continue;
+        DevCtx& c = g_ctx[d];
+        CK(cudaSetDevice(c.dev));
+        const u64* arr[BNP_NARR] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        for (auto& in : ins) {
+            int rc = copy_in(c, in.which, in.host, in.K, n, parts[d].off, parts[d].cnt);
+            if (rc) return rc;
+            arr[in.which] = c.stage[in.which];
+        }
+        int rc = ensure_stage(c, 3, K_out * 32 * parts[d].cnt);
+        if (rc) return rc;
+        rc = launch(c, prog, nullptr, arr[0], arr[1], arr[2], arr[4], c.stage[3], parts[d].cnt);
+        if (rc) return rc;
+        rc = copy_out(c, 3, out, K_out, n, parts[d].off, parts[d].cnt);
+        if (rc) return rc;
+    }
+    return sync_all();
+}
+
+std::string prog_name(const char* base, int k, int variant) {
+    std::string s(base);
+    if (k > 1) s += "_x" + std::to_string(k);
+    if (variant >= 0) s += "_v" + std::to_string(variant);
+    return s;
+}
+
+int product_dev_locked(DevCtx& c, void* stream, u64* buf, u64* out, size_t n) {
+    // tree product in place: buf[i] *= buf[i + m], m = ceil(len/2)
+    size_t len = n;
+    while (len > 1) {
+        size_t m = (len + 1) / 2;
+        size_t pairs = len - m;
+        int rc = launch(c, "fq12_mul", stream, nullptr, nullptr, buf, buf + m, buf, pairs, n);
+        if (rc) return rc;
+        len = m;
+    }
+    cudaStream_t st = stream ? (cudaStream_t)stream : c.stream;
+    CK(cudaMemcpy2DAsync(out, 8, buf, n * 8, 8, 48, cudaMemcpyDeviceToDevice, st));
+    return BNP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bnp_init(const int* devices, int n_devices) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_last_error = e != cudaSuccess ? cudaGetErrorString(e) : "no CUDA device";
+        return BNP_ENODEV;
+    }
+    int zero = 0;
+    if (!devices) {
+        devices = &zero;
+        n_devices = 1;
+    }
+    if (n_devices < 1) return BNP_EINVAL;
+    for (int i = 0; i < n_devices; i++) {
+        if (devices[i] < 0 || devices[i] >= count) return BNP_EINVAL;
+        int rc = init_device(devices[i]);
+        if (rc) return rc;
+    }
+    return BNP_OK;
+}
+
+void bnp_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& c : g_ctx) {
+        if (cudaSetDevice(c.dev) != cudaSuccess) continue;
+        cudaStreamSynchronize(c.stream);
+        for (auto p : c.d_prog)
+            if (p) cudaFree(p);
+        if (c.scratch) cudaFree(c.scratch);
+        for (int i = 0; i < BNP_NARR; i++)
+            if (c.stage[i]) cudaFree(c.stage[i]);
+        cudaStreamDestroy(c.stream);
+    }
+    g_ctx.clear();
+}
+
+int bnp_device_count(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return (int)g_ctx.size();
+}
+
+const char* bnp_strerror(int code) {
+    switch (code) {
+        case BNP_OK: return "ok";
+        case BNP_EINVAL: return "invalid argument";
+        case BNP_ENODEV: return "no CUDA device / bnp_init not called";
+        case BNP_ECUDA: return "CUDA error";
+        case BNP_ENOMEM: return "out of memory";
+        case BNP_EUNSUPPORTED: return "unsupported";
+        default: return "unknown error";
+    }
+}
+
+const char* bnp_last_error(void) { return g_last_error.c_str(); }
+
+int bnp_miller_loop_batch(const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n) {
+    return run_host("miller", {{0, g1, 2}, {1, g2, 4}}, out, 12, n);
+}
+
+int bnp_multi_miller_loop_batch(const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n, int k) {
+    if (k < 1 || k > 4) return BNP_EUNSUPPORTED;
+    return run_host(prog_name("miller", k, -1).c_str(), {{0, g1, (size_t)2 * k}, {1, g2, (size_t)4 * k}}, out, 12, n);
+}
+
+int bnp_final_exp_batch(const uint64_t* in, uint64_t* out, size_t n, int variant) {
+    if (variant != 0 && variant != 1) return BNP_EINVAL;
+    return run_host(prog_name("final_exp", 1, variant).c_str(), {{2, in, 12}}, out, 12, n);
+}
+
+int bnp_pairing_batch(const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n, int variant) {
+    if (variant != 0 && variant != 1) return BNP_EINVAL;
+    return run_host(prog_name("pairing", 1, variant).c_str(), {{0, g1, 2}, {1, g2, 4}}, out, 12, n);
+}
+
+int bnp_multi_pairing_batch(const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n, int k, int variant) {
+    if (variant != 0 && variant != 1) return BNP_EINVAL;
+    if (k < 1 || k > 4) return BNP_EUNSUPPORTED;
+    return run_host(prog_name("pairing", k, variant).c_str(), {{0, g1, (size_t)2 * k}, {1, g2, (size_t)4 * k}}, out, 12,
+                    n);
+}
+
+int bnp_frobenius_batch(const uint64_t* in, uint64_t* out, size_t n, size_t power) {
+    std::string name = "frobenius_" + std::to_string(power % 12);
+    return run_host(name.c_str(), {{2, in, 12}}, out, 12, n);
+}
+
+int bnp_fq12_mul_batch(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+    return run_host("fq12_mul", {{2, a, 12}, {4, b, 12}}, out, 12, n);
+}
+
+int bnp_pairing_product(const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n, int variant) {
+    if (variant != 0 && variant != 1) return BNP_EINVAL;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ctx.empty()) return BNP_ENODEV;
+    if (n == 0 || !g1 || !g2 || !out) return BNP_EINVAL;
+    auto parts = split_range(n, g_ctx.size());
+    DevCtx& c0 = g_ctx[0];
+    // per-device: fused Miller values -> tree product -> one Fq12 (384 B) per device
+    size_t nparts = 0;
+    for (size_t d = 0; d < g_ctx.size(); d++)
+        if (parts[d].cnt) nparts++;
+    CK(cudaSetDevice(c0.dev));
+    int rc = ensure_stage(c0, 4, 384 * std::max<size_t>(nparts, 1));  // gathered partials [12][4][nparts]
+    if (rc) return rc;
+    std::vector<u64*> partial(g_ctx.size(), nullptr);
+    size_t slot = 0;
+    for (size_t d = 0; d < g_ctx.size(); d++) {
+        if (parts[d].cnt == 0) continue;
+        DevCtx& c = g_ctx[d];
+        CK(cudaSetDevice(c.dev));
+        if ((rc = copy_in(c, 0, g1, 2, n, parts[d].off, parts[d].cnt))) return rc;
+        if ((rc = copy_in(c, 1, g2, 4, n, parts[d].off, parts[d].cnt))) return rc;
+        if ((rc = ensure_stage(c, 3, 384 * parts[d].cnt))) return rc;
+        if ((rc = ensure_stage(c, 2, 384))) return rc;
+        if ((rc = launch(c, "miller_fused", nullptr, c.stage[0], c.stage[1], nullptr, nullptr, c.stage[3], parts[d].cnt)))
+            return rc;
+        if ((rc = product_dev_locked(c, nullptr, c.stage[3], c.stage[2], parts[d].cnt))) return rc;
+        partial[d] = c.stage[2];
+        slot++;
+    }
+    // gather: 48 u64 rows of one element each, into column `slot` of c0.stage[4] ([48][nparts])
+    if ((rc = sync_all())) return rc;
+    slot = 0;
+    CK(cudaSetDevice(c0.dev));
+    for (size_t d = 0; d < g_ctx.size(); d++) {
+        if (!partial[d]) continue;
+        // peer copy over NVLink (falls back to staging through the host inside the driver if P2P is off)
+        if (g_ctx[d].dev == c0.dev) {
+            CK(cudaMemcpy2DAsync(c0.stage[4] + slot, nparts * 8, partial[d], 8, 8, 48, cudaMemcpyDeviceToDevice, c0.stream));
+        } else {
+            CK(cudaMemcpyPeer(c0.stage[2], c0.dev, partial[d], g_ctx[d].dev, 384));
+            CK(cudaMemcpy2DAsync(c0.stage[4] + slot, nparts * 8, c0.stage[2], 8, 8, 48, cudaMemcpyDeviceToDevice, c0.stream));
+            CK(cudaStreamSynchronize(c0.stream));
+        }
+        slot++;
+    }
+    if ((rc = ensure_stage(c0, 3, 384))) return rc;
+    if ((rc = ensure_stage(c0, 2, 384))) return rc;
+    if ((rc = product_dev_locked(c0, nullptr, c0.stage[4], c0.stage[2], nparts))) return rc;
+    if ((rc = launch(c0, prog_name("final_exp", 1, variant).c_str(), nullptr, nullptr, nullptr, c0.stage[2], nullptr,
+                     c0.stage[3], 1)))
+        return rc;
+    CK(cudaMemcpyAsync(out, c0.stage[3], 384, cudaMemcpyDeviceToHost, c0.stream));
+    return sync_all();
+}
+
+// ---- device-pointer variants ----
+#define DEV_PROLOGUE                                 \
+    std::lock_guard<std::mutex> lk(g_mu);            \
+    DevCtx* c = find_ctx(device);                    \
+    if (!c) return BNP_ENODEV;
+
+int bnp_miller_loop_dev(int device, void* stream, const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n, int k) {
+    DEV_PROLOGUE
+    if (k < 1 || k > 4) return BNP_EUNSUPPORTED;
+    return launch(*c, prog_name("miller", k, -1).c_str(), stream, g1, g2, nullptr, nullptr, out, n);
+}
+
+int bnp_miller_loop_fused_dev(int device, void* stream, const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n) {
+    DEV_PROLOGUE
+    return launch(*c, "miller_fused", stream, g1, g2, nullptr, nullptr, out, n);
+}
+
+int bnp_final_exp_dev(int device, void* stream, const uint64_t* in, uint64_t* out, size_t n, int variant) {
+    DEV_PROLOGUE
+    if (variant != 0 && variant != 1) return BNP_EINVAL;
+    return launch(*c, prog_name("final_exp", 1, variant).c_str(), stream, nullptr, nullptr, in, nullptr, out, n);
+}
+
+int bnp_pairing_dev(int device, void* stream, const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n, int k,
+                    int variant) {
+    DEV_PROLOGUE
+    if (variant != 0 && variant != 1) return BNP_EINVAL;
+    if (k < 1 || k > 4) return BNP_EUNSUPPORTED;
+    return launch(*c, prog_name("pairing", k, variant).c_str(), stream, g1, g2, nullptr, nullptr, out, n);
+}
+
+int bnp_frobenius_dev(int device, void* stream, const uint64_t* in, uint64_t* out, size_t n, size_t power) {
+    DEV_PROLOGUE
+    std::string name = "frobenius_" + std::to_string(power % 12);
+    return launch(*c, name.c_str(), stream, nullptr, nullptr, in, nullptr, out, n);
+}
+
+int bnp_fq12_mul_dev(int device, void* stream, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+    DEV_PROLOGUE
+    return launch(*c, "fq12_mul", stream, nullptr, nullptr, a, b, out, n);
+}
+
+int bnp_fq12_product_dev(int device, void* stream, uint64_t* buf, uint64_t* out, size_t n) {
+    DEV_PROLOGUE
+    if (n == 0) return BNP_EINVAL;
+    CK(cudaSetDevice(c->dev));
+    return product_dev_locked(*c, stream, buf, out, n);
+}
+
+int bnp_run_program_dev(int device, void* stream, const char* program, const uint64_t* g1, const uint64_t* g2,
+                        const uint64_t* f12, const uint64_t* aux, uint64_t* out, size_t n) {
+    DEV_PROLOGUE
+    return launch(*c, program, stream, g1, g2, f12, aux, out, n);
+}
+
+uint64_t bnp_program_macs(const char* program) {
+    const BnpProgram* p = find_program(program);
+    return p ? p->macs : 0;
+}
+
+uint64_t bnp_launch_count(void) { return g_launches.load(); }
+
+int bnp_set_launch_config(int threads_per_block, int) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (threads_per_block == 0) return BNP_OK;
+    if (threads_per_block != 32 && threads_per_block != 64 && threads_per_block != 128) return BNP_EINVAL;
+    g_threads_per_block = threads_per_block;
+    return BNP_OK;
+}
+
+int bnp_imad_peak(int device, double* macs_per_s) {
+    DEV_PROLOGUE
+    if (!macs_per_s) return BNP_EINVAL;
+    CK(cudaSetDevice(c->dev));
+    const unsigned blocks = (unsigned)c->sm_count * 8, threads = 256;
+    const u32 iters = 1u << 14;
+    u32* d_out = nullptr;
+    CK(cudaMalloc(&d_out, (size_t)blocks * threads * 4));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        CK(cudaEventRecord(e0, c->stream));
+        bnp_imad_peak_kernel<<<blocks, threads, 0, c->stream>>>(d_out, iters, 12345u + rep);
+        CK(cudaEventRecord(e1, c->stream));
+        CK(cudaEventSynchronize(e1));
+        g_launches++;
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double macs = (double)blocks * threads * (double)iters * 24.0;
+        if (rep > 0) best = std::max(best, macs / (ms * 1e-3));
+    }
+    CK(cudaEventDestroy(e0));
+    CK(cudaEventDestroy(e1));
+    CK(cudaFree(d_out));
+    *macs_per_s = best;
+    return BNP_OK;
+}
+
+}  // extern "C"

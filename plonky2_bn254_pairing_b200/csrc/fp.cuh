@@ -1,0 +1,361 @@
+// BN254 base-field arithmetic for sm_100a: 8 x 32-bit limbs, Montgomery form with R = 2^256
+// (bit-identical to ark-ff's `Fp<MontBackend<FqConfig,4>>` 4 x u64 limbs, little endian).
+//
+// Every 32x32->64 multiply-accumulate is written as a `mad.lo.cc` / `madc.hi.cc` PAIR into two
+// adjacent registers so that ptxas fuses the pair into ONE `IMAD.WIDE.U32.X Rd, Pc, Ra, Rb, Rd, Pc`
+// (carry in/out in a predicate): one FMA-pipe issue per MAC.  To make every pair register-aligned the
+// running sum is kept in two accumulators: E holds 64-bit columns at even limb positions, O at odd
+// positions (O[k] is limb k+1).  The value is E + (O << 32); they are merged once per product.
+//
+// Carry discipline: the PTX condition code never crosses an asm statement.
+#pragma once
+#include <stdint.h>
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+// p = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+#define BNP_P0 0xd87cfd47
+#define BNP_P1 0x3c208c16
+#define BNP_P2 0x6871ca8d
+#define BNP_P3 0x97816a91
+#define BNP_P4 0x8181585d
+#define BNP_P5 0xb85045b6
+#define BNP_P6 0xe131a029
+#define BNP_P7 0x30644e72
+#define BNP_N0INV 0xe4866389  // -p^-1 mod 2^32
+
+#define BNP_STR2(x) #x
+#define BNP_STR(x) BNP_STR2(x)
+
+__device__ __constant__ u32 BNP_P[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u,
+                                        0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+
+// ---------------------------------------------------------------------------------------------
+// column chains: x[B .. B+7] (+)= s * (q0, q1, q2, q3), four 64-bit columns with carry between them
+// ---------------------------------------------------------------------------------------------
+
+// all eight limbs fresh: four independent wide products
+template <int B>
+__device__ __forceinline__ void chain_fresh(u32* x, u32 s, u32 q0, u32 q1, u32 q2, u32 q3) {
+    asm("mul.lo.u32 %0, %8, %9;  mul.hi.u32 %1, %8, %9;\n\t"
+        "mul.lo.u32 %2, %8, %10; mul.hi.u32 %3, %8, %10;\n\t"
+        "mul.lo.u32 %4, %8, %11; mul.hi.u32 %5, %8, %11;\n\t"
+        "mul.lo.u32 %6, %8, %12; mul.hi.u32 %7, %8, %12;"
+        : "=r"(x[B]), "=r"(x[B + 1]), "=r"(x[B + 2]), "=r"(x[B + 3]), "=r"(x[B + 4]), "=r"(x[B + 5]),
+          "=r"(x[B + 6]), "=r"(x[B + 7])
+        : "r"(s), "r"(q0), "r"(q1), "r"(q2), "r"(q3));
+}
+
+// limbs B..B+5 hold data, B+6 and B+7 are fresh (no carry out possible)
+template <int B>
+__device__ __forceinline__ void chain_top2(u32* x, u32 s, u32 q0, u32 q1, u32 q2, u32 q3) {
+    asm("mad.lo.cc.u32  %0, %8, %9,  %0; madc.hi.cc.u32 %1, %8, %9,  %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %10, %2; madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %8, %11, %4; madc.hi.cc.u32 %5, %8, %11, %5;\n\t"
+        "madc.lo.cc.u32 %6, %8, %12, 0;  madc.hi.u32    %7, %8, %12, 0;"
+        : "+r"(x[B]), "+r"(x[B + 1]), "+r"(x[B + 2]), "+r"(x[B + 3]), "+r"(x[B + 4]), "+r"(x[B + 5]),
+          "=r"(x[B + 6]), "=r"(x[B + 7])
+        : "r"(s), "r"(q0), "r"(q1), "r"(q2), "r"(q3));
+}
+
+// limbs B..B+6 hold data (B+6 is a captured carry, 0 or 1), B+7 is fresh (no carry out possible)
+template <int B>
+__device__ __forceinline__ void chain_top1(u32* x, u32 s, u32 q0, u32 q1, u32 q2, u32 q3) {
+    asm("mad.lo.cc.u32  %0, %8, %9,  %0; madc.hi.cc.u32 %1, %8, %9,  %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %10, %2; madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %8, %11, %4; madc.hi.cc.u32 %5, %8, %11, %5;\n\t"
+        "madc.lo.cc.u32 %6, %8, %12, %6; madc.hi.u32    %7, %8, %12, 0;"
+        : "+r"(x[B]), "+r"(x[B + 1]), "+r"(x[B + 2]), "+r"(x[B + 3]), "+r"(x[B + 4]), "+r"(x[B + 5]),
+          "+r"(x[B + 6]), "=r"(x[B + 7])
+        : "r"(s), "r"(q0), "r"(q1), "r"(q2), "r"(q3));
+}
+
+// all eight limbs hold data; the carry out is captured into the fresh limb B+8
+template <int B>
+__device__ __forceinline__ void chain_full(u32* x, u32 s, u32 q0, u32 q1, u32 q2, u32 q3) {
+    asm("mad.lo.cc.u32  %0, %9, %10, %0; madc.hi.cc.u32 %1, %9, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %11, %2; madc.hi.cc.u32 %3, %9, %11, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %12, %4; madc.hi.cc.u32 %5, %9, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %9, %13, %6; madc.hi.cc.u32 %7, %9, %13, %7;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "+r"(x[B]), "+r"(x[B + 1]), "+r"(x[B + 2]), "+r"(x[B + 3]), "+r"(x[B + 4]), "+r"(x[B + 5]),
+          "+r"(x[B + 6]), "+r"(x[B + 7]), "=r"(x[B + 8])
+        : "r"(s), "r"(q0), "r"(q1), "r"(q2), "r"(q3));
+}
+
+// ---------------------------------------------------------------------------------------------
+// 256 x 256 -> 512-bit product, 64 IMAD.WIDE + 7 carry captures + 15 merge adds
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fp_mul_wide(u32* r /*16*/, const u32* a /*8*/, const u32* b /*8*/) {
+    u32 E[16], O[16];
+    // row 0
+    chain_fresh<0>(E, a[0], b[0], b[2], b[4], b[6]);
+    chain_fresh<0>(O, a[0], b[1], b[3], b[5], b[7]);
+    // row 1: even limbs of b land on odd positions (O base 0), odd limbs on even positions (E base 2)
+    chain_full<0>(O, a[1], b[0], b[2], b[4], b[6]);
+    chain_top2<2>(E, a[1], b[1], b[3], b[5], b[7]);
+    // row 2
+    chain_full<2>(E, a[2], b[0], b[2], b[4], b[6]);
+    chain_top1<2>(O, a[2], b[1], b[3], b[5], b[7]);
+    // row 3
+    chain_full<2>(O, a[3], b[0], b[2], b[4], b[6]);
+    chain_top1<4>(E, a[3], b[1], b[3], b[5], b[7]);
+    // row 4
+    chain_full<4>(E, a[4], b[0], b[2], b[4], b[6]);
+    chain_top1<4>(O, a[4], b[1], b[3], b[5], b[7]);
+    // row 5
+    chain_full<4>(O, a[5], b[0], b[2], b[4], b[6]);
+    chain_top1<6>(E, a[5], b[1], b[3], b[5], b[7]);
+    // row 6
+    chain_full<6>(E, a[6], b[0], b[2], b[4], b[6]);
+    chain_top1<6>(O, a[6], b[1], b[3], b[5], b[7]);
+    // row 7
+    chain_full<6>(O, a[7], b[0], b[2], b[4], b[6]);
+    chain_top1<8>(E, a[7], b[1], b[3], b[5], b[7]);
+    // merge: r = E + (O << 32)
+    r[0] = E[0];
+    asm("add.cc.u32  %0, %15, %30;\n\t"
+        "addc.cc.u32 %1, %16, %31;\n\t"
+        "addc.cc.u32 %2, %17, %32;\n\t"
+        "addc.cc.u32 %3, %18, %33;\n\t"
+        "addc.cc.u32 %4, %19, %34;\n\t"
+        "addc.cc.u32 %5, %20, %35;\n\t"
+        "addc.cc.u32 %6, %21, %36;\n\t"
+        "addc.cc.u32 %7, %22, %37;\n\t"
+        "addc.cc.u32 %8, %23, %38;\n\t"
+        "addc.cc.u32 %9, %24, %39;\n\t"
+        "addc.cc.u32 %10, %25, %40;\n\t"
+        "addc.cc.u32 %11, %26, %41;\n\t"
+        "addc.cc.u32 %12, %27, %42;\n\t"
+        "addc.cc.u32 %13, %28, %43;\n\t"
+        "addc.u32    %14, %29, %44;"
+        : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]),
+          "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]), "r"(O[0]), "r"(O[1]),
+          "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]), "r"(O[9]), "r"(O[10]),
+          "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Montgomery reduction rows.  Row i clears limb i of (E + O<<32) by adding m_i * p * 2^(32 i).
+// The limb being cleared lives half in E and half in O; their sum s gives m_i, and the carry of
+// that sum enters the chain that starts one limb higher.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void redc_row0(u32* E, u32* O) {
+    u32 m, junk;
+    asm("mul.lo.u32 %17, %0, " BNP_STR(BNP_N0INV) ";\n\t"
+        // O base 0, odd limbs of p, all fresh
+        "mul.lo.u32 %9,  %17, " BNP_STR(BNP_P1) "; mul.hi.u32 %10, %17, " BNP_STR(BNP_P1) ";\n\t"
+        "mul.lo.u32 %11, %17, " BNP_STR(BNP_P3) "; mul.hi.u32 %12, %17, " BNP_STR(BNP_P3) ";\n\t"
+        "mul.lo.u32 %13, %17, " BNP_STR(BNP_P5) "; mul.hi.u32 %14, %17, " BNP_STR(BNP_P5) ";\n\t"
+        "mul.lo.u32 %15, %17, " BNP_STR(BNP_P7) "; mul.hi.u32 %16, %17, " BNP_STR(BNP_P7) ";\n\t"
+        // E base 0, even limbs of p, all data, carry -> E[8]
+        "mad.lo.cc.u32  %18, %17, " BNP_STR(BNP_P0) ", %0; madc.hi.cc.u32 %1, %17, " BNP_STR(BNP_P0) ", %1;\n\t"
+        "madc.lo.cc.u32 %2,  %17, " BNP_STR(BNP_P2) ", %2; madc.hi.cc.u32 %3, %17, " BNP_STR(BNP_P2) ", %3;\n\t"
+        "madc.lo.cc.u32 %4,  %17, " BNP_STR(BNP_P4) ", %4; madc.hi.cc.u32 %5, %17, " BNP_STR(BNP_P4) ", %5;\n\t"
+        "madc.lo.cc.u32 %6,  %17, " BNP_STR(BNP_P6) ", %6; madc.hi.cc.u32 %7, %17, " BNP_STR(BNP_P6) ", %7;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "+r"(E[0]), "+r"(E[1]), "+r"(E[2]), "+r"(E[3]), "+r"(E[4]), "+r"(E[5]), "+r"(E[6]), "+r"(E[7]),
+          "=r"(E[8]), "=r"(O[0]), "=r"(O[1]), "=r"(O[2]), "=r"(O[3]), "=r"(O[4]), "=r"(O[5]), "=r"(O[6]),
+          "=r"(O[7]), "=&r"(m), "=r"(junk));
+}
+
+// A: accumulator whose column starts AT the limb being cleared (entries A[B..B+7] all data, carry -> A[B+8]).
+// C: accumulator whose chain starts one limb higher (entries C[D..D+6] data, C[D+7] fresh); its other
+//    contribution to the cleared limb is the single entry `hi` (already final).
+template <int B, int D>
+__device__ __forceinline__ void redc_row(u32* A, u32* C, u32 hi) {
+    u32 m, s, junk;
+    asm("add.cc.u32 %18, %0, %20;\n\t"
+        "mul.lo.u32 %17, %18, " BNP_STR(BNP_N0INV) ";\n\t"
+        // chain one limb higher: odd limbs of p, carry-in from the add above
+        "madc.lo.cc.u32 %9,  %17, " BNP_STR(BNP_P1) ", %9;  madc.hi.cc.u32 %10, %17, " BNP_STR(BNP_P1) ", %10;\n\t"
+        "madc.lo.cc.u32 %11, %17, " BNP_STR(BNP_P3) ", %11; madc.hi.cc.u32 %12, %17, " BNP_STR(BNP_P3) ", %12;\n\t"
+        "madc.lo.cc.u32 %13, %17, " BNP_STR(BNP_P5) ", %13; madc.hi.cc.u32 %14, %17, " BNP_STR(BNP_P5) ", %14;\n\t"
+        "madc.lo.cc.u32 %15, %17, " BNP_STR(BNP_P7) ", %15; madc.hi.u32    %16, %17, " BNP_STR(BNP_P7) ", 0;\n\t"
+        // chain at the cleared limb: even limbs of p; low word becomes zero and is dropped
+        "mad.lo.cc.u32  %19, %17, " BNP_STR(BNP_P0) ", %18; madc.hi.cc.u32 %1, %17, " BNP_STR(BNP_P0) ", %1;\n\t"
+        "madc.lo.cc.u32 %2,  %17, " BNP_STR(BNP_P2) ", %2;  madc.hi.cc.u32 %3, %17, " BNP_STR(BNP_P2) ", %3;\n\t"
+        "madc.lo.cc.u32 %4,  %17, " BNP_STR(BNP_P4) ", %4;  madc.hi.cc.u32 %5, %17, " BNP_STR(BNP_P4) ", %5;\n\t"
+        "madc.lo.cc.u32 %6,  %17, " BNP_STR(BNP_P6) ", %6;  madc.hi.cc.u32 %7, %17, " BNP_STR(BNP_P6) ", %7;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "+r"(A[B]), "+r"(A[B + 1]), "+r"(A[B + 2]), "+r"(A[B + 3]), "+r"(A[B + 4]), "+r"(A[B + 5]),
+          "+r"(A[B + 6]), "+r"(A[B + 7]), "=r"(A[B + 8]), "+r"(C[D]), "+r"(C[D + 1]), "+r"(C[D + 2]),
+          "+r"(C[D + 3]), "+r"(C[D + 4]), "+r"(C[D + 5]), "+r"(C[D + 6]), "=r"(C[D + 7]), "=&r"(m), "=&r"(s),
+          "=r"(junk)
+        : "r"(hi));
+}
+
+// r = (r >= p) ? r - p : r      (r < 2p on entry)
+__device__ __forceinline__ void fp_cond_sub_p(u32* r) {
+    u32 t[8], borrow;
+    asm("sub.cc.u32  %0, %9,  " BNP_STR(BNP_P0) ";\n\t"
+        "subc.cc.u32 %1, %10, " BNP_STR(BNP_P1) ";\n\t"
+        "subc.cc.u32 %2, %11, " BNP_STR(BNP_P2) ";\n\t"
+        "subc.cc.u32 %3, %12, " BNP_STR(BNP_P3) ";\n\t"
+        "subc.cc.u32 %4, %13, " BNP_STR(BNP_P4) ";\n\t"
+        "subc.cc.u32 %5, %14, " BNP_STR(BNP_P5) ";\n\t"
+        "subc.cc.u32 %6, %15, " BNP_STR(BNP_P6) ";\n\t"
+        "subc.cc.u32 %7, %16, " BNP_STR(BNP_P7) ";\n\t"
+        "subc.u32    %8, 0, 0;"
+        : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]),
+          "=r"(borrow)
+        : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]));
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = borrow ? r[i] : t[i];
+}
+
+// Montgomery reduction of a 512-bit T < p * 2^256: r = T / 2^256 mod p, canonical.
+// 8 IMAD + 64 IMAD.WIDE.
+__device__ __forceinline__ void fp_redc(u32* r /*8*/, const u32* T /*16*/) {
+    u32 E[17], O[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) E[i] = T[i];
+    redc_row0(E, O);                 // clears limb 0
+    redc_row<0, 2>(O, E, E[1]);      // row 1: limb 1 = O[0] + E[1];  O chain base 0, E chain base 2
+    redc_row<2, 2>(E, O, O[1]);      // row 2: limb 2 = E[2] + O[1];  E chain base 2, O chain base 2
+    redc_row<2, 4>(O, E, E[3]);      // row 3
+    redc_row<4, 4>(E, O, O[3]);      // row 4
+    redc_row<4, 6>(O, E, E[5]);      // row 5
+    redc_row<6, 6>(E, O, O[5]);      // row 6
+    redc_row<6, 8>(O, E, E[7]);      // row 7
+    // result limbs k = 0..7: E[8+k] + O[7+k] + T[8+k]
+    u32 u[8];
+    asm("add.cc.u32  %0, %8,  %16;\n\t"
+        "addc.cc.u32 %1, %9,  %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32    %7, %15, %23;"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+        : "r"(E[8]), "r"(E[9]), "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]),
+          "r"(O[7]), "r"(O[8]), "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
+    asm("add.cc.u32  %0, %8,  %16;\n\t"
+        "addc.cc.u32 %1, %9,  %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32    %7, %15, %23;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(T[8]),
+          "r"(T[9]), "r"(T[10]), "r"(T[11]), "r"(T[12]), "r"(T[13]), "r"(T[14]), "r"(T[15]));
+    fp_cond_sub_p(r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 256-bit and 512-bit add / sub helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 add8(u32* r, const u32* a, const u32* b) {  // returns carry
+    u32 c;
+    asm("add.cc.u32  %0, %9,  %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32    %8, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]),
+          "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return c;
+}
+
+__device__ __forceinline__ u32 sub8(u32* r, const u32* a, const u32* b) {  // returns 0 or 0xffffffff (borrow)
+    u32 c;
+    asm("sub.cc.u32  %0, %9,  %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32    %8, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]),
+          "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return c;
+}
+
+// r += p & mask   (mask is 0 or 0xffffffff)
+__device__ __forceinline__ void add_p_masked(u32* r, u32 mask) {
+    asm("add.cc.u32  %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\t"
+        "addc.cc.u32 %3, %3, %11;\n\t"
+        "addc.cc.u32 %4, %4, %12;\n\t"
+        "addc.cc.u32 %5, %5, %13;\n\t"
+        "addc.cc.u32 %6, %6, %14;\n\t"
+        "addc.u32    %7, %7, %15;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+        : "r"(mask & (u32)BNP_P0), "r"(mask & (u32)BNP_P1), "r"(mask & (u32)BNP_P2), "r"(mask & (u32)BNP_P3),
+          "r"(mask & (u32)BNP_P4), "r"(mask & (u32)BNP_P5), "r"(mask & (u32)BNP_P6), "r"(mask & (u32)BNP_P7));
+}
+
+// 512-bit r = a - b, returns borrow mask
+__device__ __forceinline__ u32 sub16(u32* r, const u32* a, const u32* b) {
+    u32 c;
+    asm("sub.cc.u32  %0, %17, %33;\n\t"
+        "subc.cc.u32 %1, %18, %34;\n\t"
+        "subc.cc.u32 %2, %19, %35;\n\t"
+        "subc.cc.u32 %3, %20, %36;\n\t"
+        "subc.cc.u32 %4, %21, %37;\n\t"
+        "subc.cc.u32 %5, %22, %38;\n\t"
+        "subc.cc.u32 %6, %23, %39;\n\t"
+        "subc.cc.u32 %7, %24, %40;\n\t"
+        "subc.cc.u32 %8, %25, %41;\n\t"
+        "subc.cc.u32 %9, %26, %42;\n\t"
+        "subc.cc.u32 %10, %27, %43;\n\t"
+        "subc.cc.u32 %11, %28, %44;\n\t"
+        "subc.cc.u32 %12, %29, %45;\n\t"
+        "subc.cc.u32 %13, %30, %46;\n\t"
+        "subc.cc.u32 %14, %31, %47;\n\t"
+        "subc.cc.u32 %15, %32, %48;\n\t"
+        "subc.u32    %16, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8]),
+          "r"(a[9]), "r"(a[10]), "r"(a[11]), "r"(a[12]), "r"(a[13]), "r"(a[14]), "r"(a[15]), "r"(b[0]), "r"(b[1]),
+          "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(b[8]), "r"(b[9]), "r"(b[10]),
+          "r"(b[11]), "r"(b[12]), "r"(b[13]), "r"(b[14]), "r"(b[15]));
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// canonical Fp ops (inputs and outputs in [0, p))
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fp_add(u32* r, const u32* a, const u32* b) {
+    add8(r, a, b);  // < 2p < 2^255: no carry
+    fp_cond_sub_p(r);
+}
+
+__device__ __forceinline__ void fp_sub(u32* r, const u32* a, const u32* b) {
+    u32 borrow = sub8(r, a, b);
+    add_p_masked(r, borrow);
+}
+
+__device__ __forceinline__ void fp_neg(u32* r, const u32* a) {
+    u32 nz = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) nz |= a[i];
+    u32 pp[8] = {(u32)BNP_P0, (u32)BNP_P1, (u32)BNP_P2, (u32)BNP_P3, (u32)BNP_P4, (u32)BNP_P5, (u32)BNP_P6, (u32)BNP_P7};
+    u32 t[8];
+    sub8(t, pp, a);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = nz ? t[i] : 0u;
+}
+
+__device__ __forceinline__ void fp_mul(u32* r, const u32* a, const u32* b) {
+    u32 T[16];
+    fp_mul_wide(T, a, b);
+    fp_redc(r, T);
+}

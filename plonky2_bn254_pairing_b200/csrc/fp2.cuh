@@ -1,0 +1,180 @@
+// Fq2 = Fq[u]/(u^2+1) on top of fp.cuh; all values canonical Montgomery residues.
+// Karatsuba with lazy reduction: an Fq2 product is 3 wide products + 2 Montgomery reductions.
+#pragma once
+#include "fp.cuh"
+
+struct Fp2 {
+    u32 c0[8];
+    u32 c1[8];
+};
+
+__device__ __forceinline__ void fp2_mul(Fp2& r, const Fp2& a, const Fp2& b) {
+    u32 sa[8], sb[8];
+    add8(sa, a.c0, a.c1);  // < 2p < 2^255
+    add8(sb, b.c0, b.c1);
+    u32 P0[16], P1[16], P2[16];
+    fp_mul_wide(P0, a.c0, b.c0);
+    fp_mul_wide(P1, a.c1, b.c1);
+    fp_mul_wide(P2, sa, sb);  // < 4p^2 < p*2^256
+    sub16(P2, P2, P0);
+    sub16(P2, P2, P1);  // a0b1 + a1b0 in [0, 2p^2)
+    u32 borrow = sub16(P0, P0, P1);
+    add_p_masked(P0 + 8, borrow);  // a0b0 - a1b1 (+ p*2^256 when negative) in [0, p*2^256)
+    fp_redc(r.c0, P0);
+    fp_redc(r.c1, P2);
+}
+
+__device__ __forceinline__ void fp2_sqr(Fp2& r, const Fp2& a) {
+    u32 s[8], d[8], t[8];
+    add8(s, a.c0, a.c1);     // a0 + a1 < 2p
+    fp_sub(d, a.c0, a.c1);   // a0 - a1 mod p
+    add8(t, a.c0, a.c0);     // 2 a0 < 2p
+    u32 W0[16], W1[16];
+    fp_mul_wide(W0, s, d);      // < 2p^2
+    fp_mul_wide(W1, t, a.c1);   // < 2p^2
+    fp_redc(r.c0, W0);
+    fp_redc(r.c1, W1);
+}
+
+// r = a * s, s in Fq
+__device__ __forceinline__ void fp2_mul_fp(Fp2& r, const Fp2& a, const u32* s) {
+    u32 W0[16], W1[16];
+    fp_mul_wide(W0, a.c0, s);
+    fp_mul_wide(W1, a.c1, s);
+    fp_redc(r.c0, W0);
+    fp_redc(r.c1, W1);
+}
+
+__device__ __forceinline__ void fp2_add(Fp2& r, const Fp2& a, const Fp2& b) {
+    fp_add(r.c0, a.c0, b.c0);
+    fp_add(r.c1, a.c1, b.c1);
+}
+
+__device__ __forceinline__ void fp2_sub(Fp2& r, const Fp2& a, const Fp2& b) {
+    fp_sub(r.c0, a.c0, b.c0);
+    fp_sub(r.c1, a.c1, b.c1);
+}
+
+__device__ __forceinline__ void fp2_neg(Fp2& r, const Fp2& a) {
+    fp_neg(r.c0, a.c0);
+    fp_neg(r.c1, a.c1);
+}
+
+__device__ __forceinline__ void fp2_conj(Fp2& r, const Fp2& a) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.c0[i] = a.c0[i];
+    fp_neg(r.c1, a.c1);
+}
+
+// v (9 limbs, v < 2^258) -> r = v mod p, canonical.  One quotient estimate from the top 32 bits
+// (q_est in {q-1, q}), one multiply-subtract, one conditional subtraction.
+__device__ __forceinline__ void fp_reduce_small(u32* r, const u32* v /*9*/) {
+    u32 h = (v[8] << 30) | (v[7] >> 2);      // floor(v / 2^226)
+    u32 q = h / 202970013u;                   // ceil(p / 2^226); q <= floor(v/p) <= q+1
+    // qp = q * p (q <= 20): 9 limbs
+    u32 E[8], O[8];
+    chain_fresh<0>(E, q, (u32)BNP_P0, (u32)BNP_P2, (u32)BNP_P4, (u32)BNP_P6);
+    chain_fresh<0>(O, q, (u32)BNP_P1, (u32)BNP_P3, (u32)BNP_P5, (u32)BNP_P7);
+    u32 qp[8];
+    qp[0] = E[0];
+    asm("add.cc.u32  %0, %7,  %14;\n\t"
+        "addc.cc.u32 %1, %8,  %15;\n\t"
+        "addc.cc.u32 %2, %9,  %16;\n\t"
+        "addc.cc.u32 %3, %10, %17;\n\t"
+        "addc.cc.u32 %4, %11, %18;\n\t"
+        "addc.cc.u32 %5, %12, %19;\n\t"
+        "addc.u32    %6, %13, %20;"
+        : "=r"(qp[1]), "=r"(qp[2]), "=r"(qp[3]), "=r"(qp[4]), "=r"(qp[5]), "=r"(qp[6]), "=r"(qp[7])
+        : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(O[0]), "r"(O[1]),
+          "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]));
+    // v - q*p < 2p < 2^255, so limb 8 of the difference is zero and limbs 0..7 suffice
+    sub8(r, v, qp);
+    fp_cond_sub_p(r);
+}
+
+// v = 9*a + c   (9 limbs), a, c < 2^256
+__device__ __forceinline__ void mul9_add(u32* v /*9*/, const u32* a, const u32* c) {
+    u32 E[9], O[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) E[i] = c[i];
+    // E columns at limbs 0,2,4,6 accumulate onto c; carry out -> E[8]
+    chain_full<0>(E, 9u, a[0], a[2], a[4], a[6]);
+    chain_fresh<0>(O, 9u, a[1], a[3], a[5], a[7]);
+    v[0] = E[0];
+    asm("add.cc.u32  %0, %8,  %16;\n\t"
+        "addc.cc.u32 %1, %9,  %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32    %7, %15, %23;"
+        : "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8])
+        : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(O[0]),
+          "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]));
+}
+
+// r = a * (9 + u) = (9 a0 - a1) + (a0 + 9 a1) u
+__device__ __forceinline__ void fp2_mul_xi(Fp2& r, const Fp2& a) {
+    const u32 pp[8] = {(u32)BNP_P0, (u32)BNP_P1, (u32)BNP_P2, (u32)BNP_P3,
+                       (u32)BNP_P4, (u32)BNP_P5, (u32)BNP_P6, (u32)BNP_P7};
+    u32 n1[8], v[9], t0[8], t1[8];
+    sub8(n1, pp, a.c1);        // p - a1 in (0, p]
+    mul9_add(v, a.c0, n1);     // 9 a0 + p - a1 < 10p
+    fp_reduce_small(t0, v);
+    mul9_add(v, a.c1, a.c0);   // 9 a1 + a0 < 10p
+    fp_reduce_small(t1, v);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        r.c0[i] = t0[i];
+        r.c1[i] = t1[i];
+    }
+}
+
+// Fq inversion by Fermat: a^(p-2).
+// Runs once or twice per pairing (easy part / Miller scale), so it is written for size, not speed.
+__device__ __noinline__ void fp_inv(u32* r, const u32* a) {
+    // p - 2, 32-bit limbs little endian
+    const u32 e[8] = {(u32)BNP_P0 - 2u, (u32)BNP_P1, (u32)BNP_P2, (u32)BNP_P3,
+                      (u32)BNP_P4, (u32)BNP_P5, (u32)BNP_P6, (u32)BNP_P7};
+    u32 acc[8], base[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) base[i] = a[i];
+    // acc = 1 in Montgomery form = R mod p
+    acc[0] = 0xc58f0d9du; acc[1] = 0xd35d438du; acc[2] = 0xf5c70b3du; acc[3] = 0x0a78eb28u;
+    acc[4] = 0x7879462cu; acc[5] = 0x666ea36fu; acc[6] = 0x9a07df2fu; acc[7] = 0x0e0a77c1u;
+    // left-to-right binary ladder; the exponent is a constant, so the multiply branch is uniform
+    // across the whole grid (no divergence).  254 squarings + popcount(p-2) multiplications.
+#pragma unroll 1
+    for (int bit = 253; bit >= 0; bit--) {
+        u32 t[8];
+        fp_mul(t, acc, acc);
+        u32 w = e[0];
+#pragma unroll
+        for (int k = 1; k < 8; k++) w = ((bit >> 5) == k) ? e[k] : w;  // no dynamic register indexing
+        if ((w >> (bit & 31)) & 1u) {
+            fp_mul(acc, t, base);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] = t[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = acc[i];
+}
+
+// r = 1 / a in Fq2: conj(a) / (a0^2 + a1^2).  Zero maps to zero (the reference panics instead).
+__device__ __forceinline__ void fp2_inv(Fp2& r, const Fp2& a) {
+    u32 W0[16], W1[16], n[8], ni[8];
+    fp_mul_wide(W0, a.c0, a.c0);
+    fp_mul_wide(W1, a.c1, a.c1);
+    u32 t0[8], t1[8];
+    fp_redc(t0, W0);
+    fp_redc(t1, W1);
+    fp_add(n, t0, t1);
+    fp_inv(ni, n);
+    u32 m1[8];
+    fp_mul(r.c0, a.c0, ni);
+    fp_mul(m1, a.c1, ni);
+    fp_neg(r.c1, m1);
+}

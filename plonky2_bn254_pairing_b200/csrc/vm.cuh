@@ -1,0 +1,233 @@
+// The Fq2 sequencer: one thread = one pairing, all threads run the same straight-line program.
+//
+// Why a sequencer instead of one giant inlined kernel (B200-first reasoning):
+//   * a fused pairing is ~27 000 Fq2-level operations; inlined that is >10^7 SASS instructions, far
+//     beyond the 32 KB L1.5 / ~40 KB L2 instruction caches.  Here every Fq2 operation exists once
+//     (~25 KB of SASS in total) and stays resident in the instruction cache;
+//   * the per-pairing state (f: 384 B, R: 192 B, lines, Karatsuba temporaries) exceeds the register
+//     file at any useful occupancy, and registers cannot be indexed dynamically.  The state lives in
+//     shared memory as 64-byte Fq2 slots laid out [slot][quad][thread] so that every access is a
+//     conflict-free LDS.128/STS.128, and registers hold only the operands of the running operation;
+//   * control flow is warp- and grid-uniform (the program counter is the same for every thread), so
+//     there is no divergence and the instruction word is fetched with a broadcast load.
+#pragma once
+#include "fp2.cuh"
+#include "microcode_ops.h"
+
+#define BNP_NARR 5
+#define BNP_MAX_CONST 128
+
+struct VmArgs {
+    const u64* prog;        // instruction words (device global memory)
+    u64* arr[BNP_NARR];     // SoA arrays: [K][4][stride] u64 (ids in microcode/isa.py)
+    uint4* scratch;         // [n_scratch][4][total_threads] uint4
+    u32 n;                  // elements to process
+    u32 stride;             // elements per limb row of the arrays (>= n)
+};
+
+__device__ __constant__ u32 BNP_CONSTS[BNP_MAX_CONST][16];
+
+template <int T>
+struct Slots {
+    uint4* base;  // shared memory, already offset by threadIdx.x
+    __device__ __forceinline__ void load(Fp2& r, u32 s) const {
+        const uint4* p = base + s * (4 * T);
+        uint4 q0 = p[0], q1 = p[T], q2 = p[2 * T], q3 = p[3 * T];
+        r.c0[0] = q0.x; r.c0[1] = q0.y; r.c0[2] = q0.z; r.c0[3] = q0.w;
+        r.c0[4] = q1.x; r.c0[5] = q1.y; r.c0[6] = q1.z; r.c0[7] = q1.w;
+        r.c1[0] = q2.x; r.c1[1] = q2.y; r.c1[2] = q2.z; r.c1[3] = q2.w;
+        r.c1[4] = q3.x; r.c1[5] = q3.y; r.c1[6] = q3.z; r.c1[7] = q3.w;
+    }
+    __device__ __forceinline__ void load_half(u32* r, u32 s, u32 half) const {
+        const uint4* p = base + s * (4 * T) + half * (2 * T);
+        uint4 q0 = p[0], q1 = p[T];
+        r[0] = q0.x; r[1] = q0.y; r[2] = q0.z; r[3] = q0.w;
+        r[4] = q1.x; r[5] = q1.y; r[6] = q1.z; r[7] = q1.w;
+    }
+    __device__ __forceinline__ void store(u32 s, const Fp2& r) const {
+        uint4* p = base + s * (4 * T);
+        p[0] = make_uint4(r.c0[0], r.c0[1], r.c0[2], r.c0[3]);
+        p[T] = make_uint4(r.c0[4], r.c0[5], r.c0[6], r.c0[7]);
+        p[2 * T] = make_uint4(r.c1[0], r.c1[1], r.c1[2], r.c1[3]);
+        p[3 * T] = make_uint4(r.c1[4], r.c1[5], r.c1[6], r.c1[7]);
+    }
+};
+
+// one Fq (4 x u64 limbs, stride n) of element e
+__device__ __forceinline__ void ldg_fp(u32* r, const u64* arr, u32 f, u32 n, u32 e) {
+    const u64* p = arr + (size_t)f * 4 * n + e;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        u64 v = __ldg(p + (size_t)j * n);
+        r[2 * j] = (u32)v;
+        r[2 * j + 1] = (u32)(v >> 32);
+    }
+}
+
+__device__ __forceinline__ void stg_fp(u64* arr, u32 f, u32 n, u32 e, const u32* r) {
+    u64* p = arr + (size_t)f * 4 * n + e;
+#pragma unroll
+    for (int j = 0; j < 4; j++) p[(size_t)j * n] = (u64)r[2 * j] | ((u64)r[2 * j + 1] << 32);
+}
+
+template <int T>
+__global__ void __launch_bounds__(T) bnp_vm_kernel(VmArgs args) {
+    extern __shared__ uint4 bnp_smem[];
+    Slots<T> S;
+    S.base = bnp_smem + threadIdx.x;
+    const u32 total = gridDim.x * T;
+    const u32 gtid = blockIdx.x * T + threadIdx.x;
+    uint4* scr = args.scratch + gtid;
+    const u32 n = args.n, stride = args.stride;
+
+    for (u32 base = blockIdx.x * T; base < n; base += total) {
+        const u32 e_raw = base + threadIdx.x;
+        const bool active = e_raw < n;
+        const u32 e = active ? e_raw : n - 1;  // idle lanes shadow the last element and never store
+        const u64* pc = args.prog;
+        u64 ins = __ldg(pc);
+        for (;;) {
+            const u64 nxt = __ldg(++pc);  // prefetch (every program ends with END followed by padding)
+            const u32 lo = (u32)ins, hi = (u32)(ins >> 32);
+            const u32 op = lo & 0xffu, d = (lo >> 8) & 0xfffu, a = lo >> 20, b = hi & 0xfffu, imm = hi >> 12;
+            if (op == BNP_OP_END) break;
+            Fp2 x, y, r;
+            switch (op) {
+                case BNP_OP_MUL:
+                    S.load(x, a);
+                    S.load(y, b);
+                    fp2_mul(r, x, y);
+                    S.store(d, r);
+                    break;
+                case BNP_OP_SQR:
+                    S.load(x, a);
+                    fp2_sqr(r, x);
+                    S.store(d, r);
+                    break;
+                case BNP_OP_MULFP: {
+                    u32 s[8];
+                    S.load(x, a);
+                    S.load_half(s, b, imm & 1u);
+                    fp2_mul_fp(r, x, s);
+                    S.store(d, r);
+                    break;
+                }
+                case BNP_OP_ADD:
+                    S.load(x, a);
+                    S.load(y, b);
+                    fp2_add(r, x, y);
+                    S.store(d, r);
+                    break;
+                case BNP_OP_SUB:
+                    S.load(x, a);
+                    S.load(y, b);
+                    fp2_sub(r, x, y);
+                    S.store(d, r);
+                    break;
+                case BNP_OP_DBL:
+                    S.load(x, a);
+                    fp2_add(r, x, x);
+                    S.store(d, r);
+                    break;
+                case BNP_OP_NEG:
+                    S.load(x, a);
+                    fp2_neg(r, x);
+                    S.store(d, r);
+                    break;
+                case BNP_OP_CONJ:
+                    S.load(x, a);
+                    fp2_conj(r, x);
+                    S.store(d, r);
+                    break;
+                case BNP_OP_MULXI:
+                    S.load(x, a);
+                    fp2_mul_xi(r, x);
+                    S.store(d, r);
+                    break;
+                case BNP_OP_MOV:
+                    S.load(x, a);
+                    S.store(d, x);
+                    break;
+                case BNP_OP_LDC:
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        r.c0[i] = BNP_CONSTS[imm][i];
+                        r.c1[i] = BNP_CONSTS[imm][8 + i];
+                    }
+                    S.store(d, r);
+                    break;
+                case BNP_OP_LDG:
+                    ldg_fp(r.c0, args.arr[imm], a, stride, e);
+                    ldg_fp(r.c1, args.arr[imm], b, stride, e);
+                    S.store(d, r);
+                    break;
+                case BNP_OP_STG:
+                    S.load(x, a);
+                    if (active) {
+                        stg_fp(args.arr[imm], d, stride, e, x.c0);
+                        stg_fp(args.arr[imm], b, stride, e, x.c1);
+                    }
+                    break;
+                case BNP_OP_SPILL: {
+                    const uint4* p = S.base + a * (4 * T);
+                    uint4* q = scr + (size_t)imm * 4 * total;
+                    q[0] = p[0];
+                    q[total] = p[T];
+                    q[2 * (size_t)total] = p[2 * T];
+                    q[3 * (size_t)total] = p[3 * T];
+                    break;
+                }
+                case BNP_OP_FILL: {
+                    uint4* p = S.base + d * (4 * T);
+                    const uint4* q = scr + (size_t)imm * 4 * total;
+                    p[0] = q[0];
+                    p[T] = q[total];
+                    p[2 * T] = q[2 * (size_t)total];
+                    p[3 * T] = q[3 * (size_t)total];
+                    break;
+                }
+                case BNP_OP_INV:
+                    S.load(x, a);
+                    fp2_inv(r, x);
+                    S.store(d, r);
+                    break;
+                default:
+                    break;
+            }
+            ins = nxt;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// IMAD.WIDE.U32 throughput microbenchmark: 6 independent carry chains of 4 MACs per iteration,
+// the same mad.lo.cc/madc.hi.cc idiom as the field code, no memory traffic in the loop.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bnp_imad_peak_kernel(u32* out, u32 iters, u32 seed) {
+    u32 x[6][8];
+    u32 s = seed + threadIdx.x, q0 = s * 3u + 1u, q1 = s * 5u + 7u, q2 = s * 7u + 3u, q3 = s * 11u + 5u;
+#pragma unroll
+    for (int c = 0; c < 6; c++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[c][i] = s + c * 8 + i;
+#pragma unroll 1
+    for (u32 it = 0; it < iters; it++) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            asm volatile(
+                "mad.lo.cc.u32  %0, %8, %9,  %0; madc.hi.cc.u32 %1, %8, %9,  %1;\n\t"
+                "madc.lo.cc.u32 %2, %8, %10, %2; madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+                "madc.lo.cc.u32 %4, %8, %11, %4; madc.hi.cc.u32 %5, %8, %11, %5;\n\t"
+                "madc.lo.cc.u32 %6, %8, %12, %6; madc.hi.u32    %7, %8, %12, %7;"
+                : "+r"(x[c][0]), "+r"(x[c][1]), "+r"(x[c][2]), "+r"(x[c][3]), "+r"(x[c][4]), "+r"(x[c][5]),
+                  "+r"(x[c][6]), "+r"(x[c][7])
+                : "r"(s), "r"(q0), "r"(q1), "r"(q2), "r"(q3));
+        }
+    }
+    u32 acc = 0;
+#pragma unroll
+    for (int c = 0; c < 6; c++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc ^= x[c][i];
+    if (acc == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = acc;  // keep the loop alive
+}

@@ -1,0 +1,341 @@
+"""The pairing-level schedules, written against builder.Builder.
+
+Reference being restated (results must be bit-identical):
+    miller_loop_BN_native        /root/reference/src/miller_loop_native.rs:112-190
+    multi_miller_loop_BN_native  /root/reference/src/miller_loop_native.rs:192-282
+    easy_part / hard_part_BN_native / final_exp_native   /root/reference/src/final_exp_native.rs:130-213
+    frobenius_map_native         /root/reference/src/final_exp_native.rs:17-54
+    pairing                      /root/reference/src/pairing.rs:20-22
+
+B200-first differences (all value-preserving):
+  * R is kept in homogeneous projective coordinates; the reference normalises to affine after every
+    step (one Fq2 inversion each, miller_loop_native.rs:157,167,186).  Our tangent line is
+    xi*Z^2/w^3 times the reference's and our chord line Z/w^2 times the reference's; the accumulated
+    factor is S * xi^a * w^-b with S in Fq2 tracked at run time and (a, b) known at build time.
+      - standalone Miller loop: one Fq2 inversion at the end restores the reference's exact value;
+      - fused pairing: the factor lies in a proper subfield and is annihilated by the easy part
+        (p^6-1)(p^2+1), so it is not tracked at all.
+  * lines are multiplied in "034" form (13 Fq2 products) instead of the reference's 18-product
+    schoolbook (miller_loop_native.rs:46-96).
+  * the hard part runs in the cyclotomic subgroup: Granger-Scott squarings, conj() for the inverse
+    (the reference divides, final_exp_native.rs:72-75), Frobenius constants from a table
+    (the reference recomputes them on every call, final_exp_native.rs:27,183-192).
+"""
+from . import isa
+from .builder import Builder, ConstPool, P, XI, BN_X, c_mul, c_pow, c_inv, naf_digits
+
+# miller_loop_native.rs:314-318
+SIX_U_PLUS_2_NAF = [
+    0, 0, 0, 1, 0, 1, 0, -1, 0, 0, 1, -1, 0, 0, 1, 0, 0, 1, 1, 0, -1, 0, 0, 1, 0, -1, 0, 0, 0, 0,
+    1, 1, 1, 0, 0, -1, 0, 0, 1, 0, 0, 0, 0, 0, -1, 0, 0, 1, 1, 0, 0, -1, 0, 0, 0, 1, 1, 0, -1, 0,
+    0, 1, 0, 1, 1,
+]
+
+# xi^((p-1)/6): `expected_c` of miller_loop_native.rs:176-178; c2, c3 at :180-181
+_C1 = c_pow(XI, (P - 1) // 6)
+_C2 = c_mul(_C1, _C1)
+_C3 = c_mul(_C2, _C1)
+
+
+class _Pair:
+    """Per-pair state of the projective Miller loop."""
+
+    def __init__(self, b, pair_index):
+        k = pair_index
+        self.b = b
+        self.Pv = b.ldg(isa.ARR_G1, 2 * k, 2 * k + 1)  # (xP, yP) packed in one slot
+        self.Qx = b.ldg(isa.ARR_G2, 4 * k, 4 * k + 1)
+        self.Qy = b.ldg(isa.ARR_G2, 4 * k + 2, 4 * k + 3)
+        # (-3 xP, -yP): scalars for the tangent's w^4 coefficient and the chord's w^2 coefficient
+        m3 = -b.times(self.Pv, 3)
+        self.Pn = m3  # c0 = -3 xP (c1 = -3 yP unused)
+        self.Pm = -self.Pv  # c1 = -yP
+        self.nQy = None
+        self.X, self.Y, self.Z = self.Qx, self.Qy, b.const((1, 0))
+
+    def neg_qy(self):
+        if self.nQy is None:
+            self.nQy = -self.Qy
+        return self.nQy
+
+    def double_step(self):
+        """Tangent at R and R <- 2R.  Returns the line as (e0, e1, e3) of  xi*Z^2/w^3 * tangent_ref:
+              tangent_ref*Z^2 = l0 + l3 w^3 + l4 w^4,  l0 = xi Y^2 - 9 Z^2, l3 = 2YZ yP, l4 = -3 X^2 xP
+              (miller_loop_native.rs:30-44 with the curve equation substituted)
+           and (e0, e1, e3) = (xi l3, xi l4, l0).
+        Doubling: Costello-Lange-Naehrig homogeneous formulas for y^2 = x^3 + 3/xi, with the whole
+        triple scaled by 4 xi^2 so that neither a halving nor the constant 3/xi is needed."""
+        b = self.b
+        X, Y, Z = self.X, self.Y, self.Z
+        B = Y.sqr()
+        C = Z.sqr()
+        J = X.sqr()
+        H = (Y * Z).dbl()  # 2YZ
+        Bx = B.mulxi()  # xi Y^2
+        E9 = b.times(C, 9)  # 9 Z^2
+        F27 = b.times(E9, 3)
+        xiH = H.mulxi()
+        l0 = Bx - E9
+        e0 = xiH.mulfp(self.Pv, 1)  # xi * 2YZ * yP
+        e1 = J.mulxi().mulfp(self.Pn, 0)  # xi * X^2 * (-3 xP)
+        XY2 = (X * Y).dbl()
+        self.X = (XY2 * (Bx - F27)).mulxi()
+        G2 = Bx + F27
+        self.Y = G2.sqr() - b.times(E9.sqr(), 12)
+        self.Z = b.times(Bx * xiH, 4)
+        return e0, e1, l0
+
+    def add_step(self, x2, y2, update=True):
+        """Chord through R and the affine point (x2, y2), then R <- R + (x2, y2).
+        Returns (e0, e1, e3) = (l2, l3, l5) of  Z/w^2 * chord_ref:
+              chord_ref*Z = l2 w^2 + l3 w^3 + l5 w^5,
+              l2 = (x2 Z - X) yP,  l3 = (Y - y2 Z) xP,  l5 = X y2 - x2 Y     (miller_loop_native.rs:10-28)"""
+        X, Y, Z = self.X, self.Y, self.Z
+        theta = Y - y2 * Z
+        lam = X - x2 * Z
+        l2 = lam.mulfp(self.Pm, 1)  # -(X - x2 Z) * yP ... (-yP) scalar
+        l3 = theta.mulfp(self.Pv, 0)
+        l5 = X * y2 - x2 * Y
+        if update:
+            c = theta.sqr()
+            d = lam.sqr()
+            e = lam * d
+            f = Z * c
+            g = X * d
+            h = e + f - g.dbl()
+            self.X = lam * h
+            self.Y = theta * (g - h) - e * Y
+            self.Z = Z * e
+        return l2, l3, l5
+
+
+def _miller_core(b, n_pairs, track_scale):
+    """Shared-squaring Miller loop over n_pairs pairs (n_pairs = 1 is miller_loop_BN_native).
+    Returns (g, S, exp_xi, exp_w): g = f_ref * S * xi^exp_xi * w^-exp_w  with S in Fq2 (None when untracked)."""
+    naf = SIX_U_PLUS_2_NAF
+    top = len(naf) - 1
+    while naf[top] == 0:
+        top -= 1
+    assert naf[top] == 1  # multi_miller_loop_BN_native asserts this (:201); R starts at +Q
+    pairs = [_Pair(b, k) for k in range(n_pairs)]
+
+    exp_xi, exp_w = 0, 0
+    S = None
+
+    def scale_tangent(pr):
+        nonlocal S
+        if track_scale:
+            z2 = pr.Z.sqr()
+            S = z2 if S is None else S * z2
+
+    def scale_chord(pr):
+        nonlocal S
+        if track_scale:
+            S = S * pr.Z
+
+    # initial f = product of the tangents at R = Q (miller_loop_native.rs:127-149, :206-233)
+    g = None
+    for pr in pairs:
+        scale_tangent(pr)
+        e0, e1, e3 = pr.double_step()
+        exp_xi += 1
+        exp_w += 3
+        if g is None:
+            zero = b.const((0, 0))
+            g = [e0, e1, zero, e3, zero, zero]
+        else:
+            g = b.fq12_mul_034(g, e0, e1, e3)
+
+    i = top - 1
+    first = True
+    while True:
+        if not first:
+            # f <- f^2, then one tangent per pair (:152-155, :238-243); R <- 2R (:157, :244-246)
+            g = b.fq12_sqr(g)
+            exp_xi *= 2
+            exp_w *= 2
+            if track_scale:
+                S = S.sqr()
+            for pr in pairs:
+                scale_tangent(pr)
+                e0, e1, e3 = pr.double_step()
+                exp_xi += 1
+                exp_w += 3
+                g = b.fq12_mul_034(g, e0, e1, e3)
+        first = False
+        if naf[i] != 0:
+            for pr in pairs:
+                y2 = pr.Qy if naf[i] == 1 else pr.neg_qy()
+                scale_chord(pr)
+                e0, e1, e3 = pr.add_step(pr.Qx, y2)
+                exp_w += 2
+                g = b.fq12_mul_034(g, e0, e1, e3)
+        if i == 0:
+            break
+        i -= 1
+
+    # Frobenius endpoints (:176-187, :266-280)
+    for pr in pairs:
+        q1x = b.const(_C2) * pr.Qx.conj()
+        q1y = b.const(_C3) * pr.Qy.conj()
+        scale_chord(pr)
+        e0, e1, e3 = pr.add_step(q1x, q1y)
+        exp_w += 2
+        g = b.fq12_mul_034(g, e0, e1, e3)
+        q2x = b.const(_C2) * q1x.conj()
+        nq2y = -(b.const(_C3) * q1y.conj())
+        scale_chord(pr)
+        e0, e1, e3 = pr.add_step(q2x, nq2y, update=False)
+        exp_w += 2
+        g = b.fq12_mul_034(g, e0, e1, e3)
+    return g, S, exp_xi, exp_w
+
+
+def _miller_exact(b, n_pairs):
+    """Miller loop whose output equals the reference's bit for bit."""
+    g, S, exp_xi, exp_w = _miller_core(b, n_pairs, track_scale=True)
+    # f_ref = g * w^exp_w / (S * xi^exp_xi);  w^exp_w = xi^(exp_w div 6) * w^(exp_w mod 6)
+    order = P * P - 1
+    k = c_pow(XI, (exp_w // 6 - exp_xi) % order)
+    corr = S.inv() * b.const(k)
+    g = b.fq12_rot(g, exp_w % 6)
+    return b.fq12_mul_fq2(g, corr)
+
+
+def _easy_part(b, a):
+    """final_exp_native.rs:195-206"""
+    f2 = b.fq12_mul(b.fq12_conj(a), b.fq12_inv(a))
+    f3 = b.fq12_frobenius(f2, 2)
+    return b.fq12_mul(f3, f2)
+
+
+def _hard_part_ref(b, m):
+    """final_exp_native.rs:130-169, in the cyclotomic subgroup."""
+    mp = b.fq12_frobenius(m, 1)
+    mp2 = b.fq12_frobenius(m, 2)
+    mp3 = b.fq12_frobenius(m, 3)
+    y0 = b.fq12_mul(mp, b.fq12_mul(mp2, mp3))
+    mx = b.fq12_pow_x_cyclo(m)
+    mxp = b.fq12_frobenius(mx, 1)
+    mx2 = b.fq12_pow_x_cyclo(mx)
+    mx2p = b.fq12_frobenius(mx2, 1)
+    y2 = b.fq12_frobenius(mx2, 2)
+    mx3 = b.fq12_pow_x_cyclo(mx2)
+    mx3p = b.fq12_frobenius(mx3, 1)
+    # y1 = conj(m), y3 = conj(mxp), y4 = conj(mx * mx2p), y5 = conj(mx2), y6 = conj(mx3 * mx3p)
+    y4c = b.fq12_mul(mx, mx2p)       # conj(y4)
+    y6c = b.fq12_mul(mx3, mx3p)      # conj(y6)
+    # T0 = y6^2 * y4 * y5 = conj(y6c^2 * y4c * mx2)
+    T0c = b.fq12_cyclo_sqr(y6c)
+    T0c = b.fq12_mul(T0c, y4c)
+    T0c = b.fq12_mul(T0c, mx2)
+    # T1 = y3 * y5 * T0 = conj(mxp * mx2 * T0c)
+    T1c = b.fq12_mul(b.fq12_mul(mxp, mx2), T0c)
+    # T0 = y2 * T0
+    T0 = b.fq12_mul_conj(y2, T0c)
+    T1 = b.fq12_conj(b.fq12_cyclo_sqr(T1c))   # T1^2
+    T1 = b.fq12_mul(T1, T0)
+    T1 = b.fq12_cyclo_sqr(T1)
+    T0 = b.fq12_mul_conj(T1, m)               # T1 * y1
+    T1 = b.fq12_mul(T1, y0)
+    T0 = b.fq12_cyclo_sqr(T0)
+    return b.fq12_mul(T0, T1)
+
+
+def _hard_part_ark(b, e):
+    """ark-ec 0.4.2 models/bn final_exponentiation hard part (Fuentes-Castaneda), restated; equals the
+    reference's result raised to 2x(6x^2+3x+1).  f^(-x) = conj(f^x) since x > 0."""
+    y0c = b.fq12_pow_x_cyclo(e)                # conj(y0)
+    y1c = b.fq12_cyclo_sqr(y0c)                # conj(y1)
+    y2c = b.fq12_cyclo_sqr(y1c)
+    y3c = b.fq12_mul(y2c, y1c)                 # conj(y3 before its own conjugation) => equals final y3
+    y3 = y3c
+    # y4 = (y3_old)^(-x) = conj(y3_old^x) = conj(conj(y3c)^x) = y3c^x
+    y4 = b.fq12_pow_x_cyclo(y3c)
+    y5 = b.fq12_cyclo_sqr(y4)
+    y6c_old = b.fq12_pow_x_cyclo(y5)           # y5^x = conj(y6_old)  => final y6 = conj(y6_old) = y5^x
+    y6 = y6c_old
+    y7 = b.fq12_mul(y6, y4)
+    y8 = b.fq12_mul(y7, y3)
+    y9 = b.fq12_mul_conj(y8, y1c)              # y8 * y1
+    y10 = b.fq12_mul(y8, y4)
+    y11 = b.fq12_mul(y10, e)
+    y12 = b.fq12_frobenius(y9, 1)
+    y13 = b.fq12_mul(y12, y11)
+    y8f = b.fq12_frobenius(y8, 2)
+    y14 = b.fq12_mul(y8f, y13)
+    y15 = b.fq12_frobenius(b.fq12_mul_conj(y9, e), 3)
+    return b.fq12_mul(y15, y14)
+
+
+def _final_exp(b, a, variant):
+    m = _easy_part(b, a)
+    return _hard_part_ref(b, m) if variant == 0 else _hard_part_ark(b, m)
+
+
+# ----------------------------------------------------------------------------- program table
+def prog_miller(b, n_pairs=1):
+    """arr G1/G2 -> OUT: reference-exact (multi_)miller_loop_native."""
+    b.st_fq12(isa.ARR_OUT, _miller_exact(b, n_pairs))
+
+
+def prog_miller_fused(b, n_pairs=1):
+    """arr G1/G2 -> OUT: Miller value up to a proper-subfield factor (input to a later final exp only)."""
+    g, _, _, _ = _miller_core(b, n_pairs, track_scale=False)
+    b.st_fq12(isa.ARR_OUT, g)
+
+
+def prog_final_exp(b, variant):
+    """arr F12 -> OUT: final_exp_native (variant 0) or the ark-compatible exponent (variant 1)."""
+    b.st_fq12(isa.ARR_OUT, _final_exp(b, b.ld_fq12(isa.ARR_F12), variant))
+
+
+def prog_pairing(b, variant, n_pairs=1):
+    """arr G1/G2 -> OUT: pairing.rs:20-22 fused in one launch (n_pairs > 1: product of pairings)."""
+    g, _, _, _ = _miller_core(b, n_pairs, track_scale=False)
+    b.st_fq12(isa.ARR_OUT, _final_exp(b, g, variant))
+
+
+def prog_frobenius(b, power):
+    b.st_fq12(isa.ARR_OUT, b.fq12_frobenius(b.ld_fq12(isa.ARR_F12), power))
+
+
+def prog_fq12_mul(b):
+    """OUT = F12 * AUX (MyFq12 `Mul`); used for product reductions."""
+    b.st_fq12(isa.ARR_OUT, b.fq12_mul(b.ld_fq12(isa.ARR_F12), b.ld_fq12(isa.ARR_AUX)))
+
+
+def prog_optest(b):
+    """One of every arithmetic opcode, for op-level GPU parity tests.  F12 holds 6 input slots; OUT gets
+    MUL, SQR, MULFP(c0), MULFP(c1), ADD, SUB, NEG, CONJ, MULXI, DBL, INV, (a*const) in 12 slots."""
+    x = b.ld_fq12(isa.ARR_F12)
+    outs = [
+        x[0] * x[1], x[2].sqr(), x[3].mulfp(x[4], 0), x[3].mulfp(x[4], 1), x[0] + x[5], x[1] - x[2],
+        -x[3], x[4].conj(), x[5].mulxi(), x[0].dbl(), x[1].inv(), x[2] * b.const(_C3),
+    ]
+    for i, v in enumerate(outs):
+        b.stg(isa.ARR_OUT, 2 * i, 2 * i + 1, v)
+
+
+PROGRAMS = [
+    # (name, build function, kwargs)
+    ("miller", prog_miller, {}),
+    ("miller_fused", prog_miller_fused, {}),
+    ("final_exp_v0", prog_final_exp, {"variant": 0}),
+    ("final_exp_v1", prog_final_exp, {"variant": 1}),
+    ("pairing_v0", prog_pairing, {"variant": 0}),
+    ("pairing_v1", prog_pairing, {"variant": 1}),
+    ("fq12_mul", prog_fq12_mul, {}),
+    ("optest", prog_optest, {}),
+] + [("frobenius_%d" % k, prog_frobenius, {"power": k}) for k in range(12)] \
+  + [("miller_x%d" % k, prog_miller, {"n_pairs": k}) for k in (2, 3, 4)] \
+  + [("pairing_x%d_v%d" % (k, v), prog_pairing, {"variant": v, "n_pairs": k}) for k in (2, 3, 4) for v in (0, 1)]
+
+
+def build_program(name, pool):
+    for n, fn, kw in PROGRAMS:
+        if n == name:
+            b = Builder(pool)
+            fn(b, **kw)
+            return b
+    raise KeyError(name)
