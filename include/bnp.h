@@ -91,6 +91,8 @@ uint64_t bnp_launch_count(void);
 /* Dependency-free IMAD.WIDE.U32 throughput microbenchmark on `device`: writes multiply-accumulates
  * per second (the roofline denominator) to *macs_per_s. */
 int bnp_imad_peak(int device, double* macs_per_s);
+/* Same loop with plain 32-bit IMAD (informational: the FMA pipe's nominal integer issue rate). */
+int bnp_imad32_peak(int device, double* imads_per_s);
 /* Run an arbitrary sequencer program by name on device arrays (test hook for op-level parity). */
 int bnp_run_program_dev(int device, void* stream, const char* program, const uint64_t* g1, const uint64_t* g2,
                         const uint64_t* f12, const uint64_t* aux, uint64_t* out, size_t n);

@@ -466,34 +466,47 @@ int bnp_set_launch_config(int threads_per_block, int) {
     return BNP_OK;
 }
 
-int bnp_imad_peak(int device, double* macs_per_s) {
-    DEV_PROLOGUE
-    if (!macs_per_s) return BNP_EINVAL;
+static int imad_peak_impl(DevCtx* c, int wide, double* per_s) {
     CK(cudaSetDevice(c->dev));
     const unsigned blocks = (unsigned)c->sm_count * 8, threads = 256;
-    const u32 iters = 1u << 14;
-    u32* d_out = nullptr;
-    CK(cudaMalloc(&d_out, (size_t)blocks * threads * 4));
+    const u32 iters = 1u << 13;
+    u64* d_out = nullptr;
+    CK(cudaMalloc(&d_out, (size_t)blocks * threads * 8));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
     double best = 0.0;
-    for (int rep = 0; rep < 5; rep++) {
+    for (int rep = 0; rep < 6; rep++) {
         CK(cudaEventRecord(e0, c->stream));
-        bnp_imad_peak_kernel<<<blocks, threads, 0, c->stream>>>(d_out, iters, 12345u + rep);
+        if (wide)
+            bnp_imad_wide_peak_kernel<<<blocks, threads, 0, c->stream>>>(d_out, iters, 12345u + rep);
+        else
+            bnp_imad_lo_peak_kernel<<<blocks, threads, 0, c->stream>>>(d_out, iters, 12345u + rep);
         CK(cudaEventRecord(e1, c->stream));
         CK(cudaEventSynchronize(e1));
         g_launches++;
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, e0, e1));
-        const double macs = (double)blocks * threads * (double)iters * 24.0;
-        if (rep > 0) best = std::max(best, macs / (ms * 1e-3));
+        const double ops = (double)blocks * threads * (double)iters * 32.0;
+        if (rep > 0) best = std::max(best, ops / (ms * 1e-3));
     }
     CK(cudaEventDestroy(e0));
     CK(cudaEventDestroy(e1));
     CK(cudaFree(d_out));
-    *macs_per_s = best;
+    *per_s = best;
     return BNP_OK;
+}
+
+int bnp_imad_peak(int device, double* macs_per_s) {
+    DEV_PROLOGUE
+    if (!macs_per_s) return BNP_EINVAL;
+    return imad_peak_impl(c, 1, macs_per_s);
+}
+
+int bnp_imad32_peak(int device, double* imads_per_s) {
+    DEV_PROLOGUE
+    if (!imads_per_s) return BNP_EINVAL;
+    return imad_peak_impl(c, 0, imads_per_s);
 }
 
 }  // extern "C"

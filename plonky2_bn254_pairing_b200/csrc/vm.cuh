@@ -200,34 +200,54 @@ __global__ void __launch_bounds__(T) bnp_vm_kernel(VmArgs args) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// IMAD.WIDE.U32 throughput microbenchmark: 6 independent carry chains of 4 MACs per iteration,
-// the same mad.lo.cc/madc.hi.cc idiom as the field code, no memory traffic in the loop.
+// Roofline denominators, measured on the box: dependency-light loops of the two multiply forms.
+//   bnp_imad_wide_peak_kernel : IMAD.WIDE.U32[.X] in 4-deep carry chains - the exact idiom of fp.cuh
+//                               (32 MACs per thread per iteration, registers only)
+//   bnp_imad_lo_peak_kernel   : plain 32-bit IMAD (informational: the pipe's nominal integer rate)
+// SASS-checked: the loop bodies are 32 IMAD.WIDE.U32[.X] / 32 IMAD and nothing else but the loop counter.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bnp_imad_peak_kernel(u32* out, u32 iters, u32 seed) {
-    u32 x[6][8];
-    u32 s = seed + threadIdx.x, q0 = s * 3u + 1u, q1 = s * 5u + 7u, q2 = s * 7u + 3u, q3 = s * 11u + 5u;
+__global__ void __launch_bounds__(256) bnp_imad_wide_peak_kernel(u64* out, u32 iters, u32 seed) {
+    u32 a = seed * 2654435761u + threadIdx.x, b = a ^ 0x9e3779b9u;
+    u64 acc[8];
 #pragma unroll
-    for (int c = 0; c < 6; c++)
-#pragma unroll
-        for (int i = 0; i < 8; i++) x[c][i] = s + c * 8 + i;
+    for (int c = 0; c < 8; c++) acc[c] = a + c;
 #pragma unroll 1
     for (u32 it = 0; it < iters; it++) {
 #pragma unroll
-        for (int c = 0; c < 6; c++) {
-            asm volatile(
-                "mad.lo.cc.u32  %0, %8, %9,  %0; madc.hi.cc.u32 %1, %8, %9,  %1;\n\t"
-                "madc.lo.cc.u32 %2, %8, %10, %2; madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
-                "madc.lo.cc.u32 %4, %8, %11, %4; madc.hi.cc.u32 %5, %8, %11, %5;\n\t"
-                "madc.lo.cc.u32 %6, %8, %12, %6; madc.hi.u32    %7, %8, %12, %7;"
-                : "+r"(x[c][0]), "+r"(x[c][1]), "+r"(x[c][2]), "+r"(x[c][3]), "+r"(x[c][4]), "+r"(x[c][5]),
-                  "+r"(x[c][6]), "+r"(x[c][7])
-                : "r"(s), "r"(q0), "r"(q1), "r"(q2), "r"(q3));
-        }
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < 8; c += 4)
+                asm volatile(
+                    "{ .reg .u32 l0,h0,l1,h1,l2,h2,l3,h3;\n\t"
+                    "mov.b64 {l0,h0}, %0; mov.b64 {l1,h1}, %1; mov.b64 {l2,h2}, %2; mov.b64 {l3,h3}, %3;\n\t"
+                    "mad.lo.cc.u32 l0, %4, %5, l0; madc.hi.cc.u32 h0, %4, %5, h0;\n\t"
+                    "madc.lo.cc.u32 l1, %4, %5, l1; madc.hi.cc.u32 h1, %4, %5, h1;\n\t"
+                    "madc.lo.cc.u32 l2, %4, %5, l2; madc.hi.cc.u32 h2, %4, %5, h2;\n\t"
+                    "madc.lo.cc.u32 l3, %4, %5, l3; madc.hi.u32 h3, %4, %5, h3;\n\t"
+                    "mov.b64 %0, {l0,h0}; mov.b64 %1, {l1,h1}; mov.b64 %2, {l2,h2}; mov.b64 %3, {l3,h3}; }"
+                    : "+l"(acc[c]), "+l"(acc[c + 1]), "+l"(acc[c + 2]), "+l"(acc[c + 3])
+                    : "r"(a), "r"(b));
     }
-    u32 acc = 0;
+    u64 x = 0;
 #pragma unroll
-    for (int c = 0; c < 6; c++)
+    for (int c = 0; c < 8; c++) x ^= acc[c];
+    if (x == 0x1234567812345678ull) out[blockIdx.x * blockDim.x + threadIdx.x] = x;  // keeps the loop alive
+}
+
+__global__ void __launch_bounds__(256) bnp_imad_lo_peak_kernel(u64* out, u32 iters, u32 seed) {
+    u32 a = seed * 2654435761u + threadIdx.x, b = a ^ 0x9e3779b9u;
+    u32 acc[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) acc ^= x[c][i];
-    if (acc == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = acc;  // keep the loop alive
+    for (int c = 0; c < 8; c++) acc[c] = a + c;
+#pragma unroll 1
+    for (u32 it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < 8; c++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[c]) : "r"(a), "r"(b));
+    }
+    u32 x = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) x ^= acc[c];
+    if (x == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = x;
 }

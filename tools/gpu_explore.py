@@ -118,14 +118,16 @@ def make_inputs(n, pool=256):
 def time_prog(lib, prog, n, g1, g2, reps=3):
     d1, d2 = dev_tensor(g1), dev_tensor(g2)
     out = torch.zeros((12, 4, n), dtype=torch.int64, device="cuda")
-    st = torch.cuda.current_stream().cuda_stream
+    torch.cuda.synchronize()
+    stream = torch.cuda.Stream()  # a real (non-default) stream so the events bracket the kernel
     best = None
     for r in range(reps + 1):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        native.check(lib.bnp_run_program_dev(0, ctypes.c_void_p(st), prog.encode(), d1.data_ptr(), d2.data_ptr(), None,
-                                             None, out.data_ptr(), n))
-        e1.record()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            native.check(lib.bnp_run_program_dev(0, ctypes.c_void_p(stream.cuda_stream), prog.encode(), d1.data_ptr(),
+                                                 d2.data_ptr(), None, None, out.data_ptr(), n))
+            e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         if r > 0:
@@ -137,16 +139,23 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=16384)
     ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--threads", type=int, nargs="*", default=[32, 64, 128])
+    ap.add_argument("--progs", nargs="*", default=["pairing_v0"])
     args = ap.parse_args()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     res = {}
     lib = native.init([0])
-    res["optest"] = optest(lib)
-    res["parity"] = pairing_parity()
+    if not args.no_parity:
+        res["optest"] = optest(lib)
+        res["parity"] = pairing_parity()
     peak = ctypes.c_double()
     native.check(lib.bnp_imad_peak(0, ctypes.byref(peak)))
     res["imad_peak_macs_per_s"] = peak.value
-    print("IMAD.WIDE peak: %.3e MAC/s" % peak.value)
+    peak32 = ctypes.c_double()
+    native.check(lib.bnp_imad32_peak(0, ctypes.byref(peak32)))
+    res["imad32_peak_per_s"] = peak32.value
+    print("IMAD.WIDE peak: %.3e MAC/s   IMAD(32) peak: %.3e /s" % (peak.value, peak32.value))
     g1, g2, Ps, Qs, i1, i2 = make_inputs(args.n)
     macs = lib.bnp_program_macs(b"pairing_v0")
     runs = []
@@ -157,9 +166,9 @@ def main():
         l2 = native.load(path) if path != native.LIB_PATH else lib
         dev0 = (ctypes.c_int * 1)(0)
         native.check(l2.bnp_init(dev0, 1), l2)
-        for T in (32, 64, 128):
+        for T in args.threads:
             native.check(l2.bnp_set_launch_config(T, 0), l2)
-            for prog in ("pairing_v0",):
+            for prog in args.progs:
                 try:
                     ms, out = time_prog(l2, prog, args.n, g1, g2)
                 except native.BnpError as ex:
