@@ -1,0 +1,118 @@
+"""The sequencer programs, executed by the big-integer interpreter (the exact instruction words the GPU
+runs, including spills/fills), against the oracle - for several shared-memory slot budgets."""
+import random
+
+import pytest
+
+import bn254_oracle as O
+from plonky2_bn254_pairing_b200.microcode import alloc, gen, interp, isa, programs
+from plonky2_bn254_pairing_b200.microcode.builder import ConstPool, naf_digits
+
+
+def run(name, arrays, n_slots):
+    pool = ConstPool()
+    b = programs.build_program(name, pool)
+    al = alloc.allocate(b.ops, n_slots)
+    for w in al.words:  # every operand field within the slot budget
+        op, d, a, bb, imm = isa.decode(w)
+        if op in ("MUL", "ADD", "SUB", "MULFP"):
+            assert max(d, a, bb) < n_slots
+        elif op in ("SQR", "NEG", "CONJ", "MULXI", "MOV", "INV", "DBL"):
+            assert max(d, a) < n_slots
+        elif op in ("SPILL",):
+            assert a < n_slots and imm < max(al.n_scratch, 1)
+        elif op in ("FILL",):
+            assert d < n_slots and imm < al.n_scratch
+    arrays = dict(arrays)
+    arrays[isa.ARR_OUT] = {}
+    interp.run(al.words, pool.values, arrays, al.n_slots, al.n_scratch)
+    return [arrays[isa.ARR_OUT][i] for i in range(12)], al
+
+
+PTS = O.seeded_points(0xB2540001, 4)
+
+
+def g1g2(pairs):
+    g1, g2 = [], []
+    for p, q in pairs:
+        g1 += [p[0], p[1]]
+        g2 += [q[0][0], q[0][1], q[1][0], q[1][1]]
+    return {isa.ARR_G1: g1, isa.ARR_G2: g2}
+
+
+@pytest.mark.parametrize("n_slots", [10, 14, 16, 24])
+def test_miller_exact(n_slots):
+    p, q = PTS[0]
+    got, _ = run("miller", g1g2([PTS[0]]), n_slots)
+    assert got == O.miller_loop_native(q, p)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("n_slots", [10, 16])
+def test_pairing_and_final_exp(variant, n_slots):
+    p, q = PTS[1]
+    m = O.miller_loop_native(q, p)
+    want = O.final_exp_native(m) if variant == 0 else O.final_exp_ark(m)
+    got, _ = run("pairing_v%d" % variant, g1g2([PTS[1]]), n_slots)
+    assert got == want
+    got, _ = run("final_exp_v%d" % variant, {isa.ARR_F12: m}, n_slots)
+    assert got == want
+
+
+def test_final_exp_on_non_miller_input():
+    """final_exp_native.rs:266-286 feeds a uniformly random Fq12."""
+    rnd = random.Random(4)
+    x = [rnd.randrange(O.P) for _ in range(12)]
+    got, _ = run("final_exp_v0", {isa.ARR_F12: x}, 14)
+    assert got == O.final_exp_native(x) == O.fq12_pow(x, (O.P ** 12 - 1) // O.R_ORDER)
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_multi_miller_and_product(k):
+    got, _ = run("miller_x%d" % k, g1g2(PTS[:k]), 16)
+    want = O.multi_miller_loop_native(PTS[:k])
+    assert got == want
+    got, _ = run("pairing_x%d_v0" % k, g1g2(PTS[:k]), 16)
+    assert got == O.final_exp_native(want)
+
+
+def test_fused_miller_differs_only_by_a_subfield_factor():
+    p, q = PTS[2]
+    got, _ = run("miller_fused", g1g2([PTS[2]]), 16)
+    assert got != O.miller_loop_native(q, p)
+    assert O.final_exp_native(got) == O.pairing(p, q)
+
+
+@pytest.mark.parametrize("power", [0, 1, 2, 3, 6, 11])
+def test_frobenius(power):
+    rnd = random.Random(power)
+    x = [rnd.randrange(O.P) for _ in range(12)]
+    got, _ = run("frobenius_%d" % power, {isa.ARR_F12: x}, 16)
+    assert got == O.frobenius_map_native(x, power)
+
+
+def test_fq12_mul_program():
+    rnd = random.Random(8)
+    x = [rnd.randrange(O.P) for _ in range(12)]
+    y = [rnd.randrange(O.P) for _ in range(12)]
+    got, _ = run("fq12_mul", {isa.ARR_F12: x, isa.ARR_AUX: y}, 16)
+    assert got == O.fq12_mul(x, y)
+
+
+def test_work_counts_not_above_survey_canonical():
+    """the shipped schedules must not do more algorithmic work than the canonical table."""
+    pool, progs = gen.build_all(16, names={"pairing_v0", "miller", "miller_fused", "final_exp_v0", "pairing_x4_v0"})
+    macs = {name: w["macs"] for name, _, w in progs}
+    assert macs["miller_fused"] <= 1.000e6
+    assert macs["miller"] <= 1.10e6
+    assert macs["final_exp_v0"] <= 1.05e6
+    assert macs["pairing_v0"] <= 2.04e6
+    assert macs["pairing_x4_v0"] <= 4.28e6
+
+
+def test_encode_decode_roundtrip_and_naf():
+    w = isa.encode("MULFP", d=5, a=1023, b=77, imm=1)
+    assert isa.decode(w) == ("MULFP", 5, 1023, 77, 1)
+    assert naf_digits(O.BN_X) == O.get_naf([O.BN_X])[:len(naf_digits(O.BN_X))]
+    assert sum(d << i for i, d in enumerate(programs.SIX_U_PLUS_2_NAF)) == 6 * O.BN_X + 2
+    assert programs.SIX_U_PLUS_2_NAF == O.SIX_U_PLUS_2_NAF
