@@ -317,6 +317,36 @@ def prog_optest(b):
         b.stg(isa.ARR_OUT, 2 * i, 2 * i + 1, v)
 
 
+def prog_opbench(b, op, count=2048):
+    """`count` back-to-back instances of one opcode over a rotating set of slots (cost-model tool)."""
+    x = b.ld_fq12(isa.ARR_F12)
+    vals = list(x)
+    for i in range(count):
+        a, c = vals[i % 6], vals[(i + 1) % 6]
+        if op == "MUL":
+            r = a * c
+        elif op == "SQR":
+            r = a.sqr()
+        elif op == "MULFP":
+            r = a.mulfp(c, i & 1)
+        elif op == "ADD":
+            r = a + c
+        elif op == "SUB":
+            r = a - c
+        elif op == "DBL":
+            r = a.dbl()
+        elif op == "NEG":
+            r = -a
+        elif op == "MULXI":
+            r = a.mulxi()
+        elif op == "LDC":
+            r = b.const((i + 2, 1)) + a  # one LDC + one ADD
+        else:
+            raise ValueError(op)
+        vals[i % 6] = r
+    b.st_fq12(isa.ARR_OUT, vals)
+
+
 PROGRAMS = [
     # (name, build function, kwargs)
     ("miller", prog_miller, {}),
@@ -327,7 +357,8 @@ PROGRAMS = [
     ("pairing_v1", prog_pairing, {"variant": 1}),
     ("fq12_mul", prog_fq12_mul, {}),
     ("optest", prog_optest, {}),
-] + [("frobenius_%d" % k, prog_frobenius, {"power": k}) for k in range(12)] \
+] + [("opbench_" + o.lower(), prog_opbench, {"op": o}) for o in ("MUL", "SQR", "MULFP", "ADD", "SUB", "DBL", "NEG", "MULXI")] \
+  + [("frobenius_%d" % k, prog_frobenius, {"power": k}) for k in range(12)] \
   + [("miller_x%d" % k, prog_miller, {"n_pairs": k}) for k in (2, 3, 4)] \
   + [("pairing_x%d_v%d" % (k, v), prog_pairing, {"variant": v, "n_pairs": k}) for k in (2, 3, 4) for v in (0, 1)]
 
