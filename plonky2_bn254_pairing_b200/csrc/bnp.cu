@@ -16,6 +16,8 @@
 
 namespace {
 
+constexpr unsigned BNP_NCOUNTERS = 1024;  // launches in flight never get near this
+
 struct DevCtx {
     int dev = -1;
     int sm_count = 0;
@@ -23,6 +25,8 @@ struct DevCtx {
     std::vector<u64*> d_prog;  // one device copy per program
     uint4* scratch = nullptr;
     size_t scratch_bytes = 0;
+    u32* counters = nullptr;   // ring of work counters, one per launch in flight
+    unsigned next_counter = 0;
     // staging for the host-pointer API
     u64* stage[BNP_NARR] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t stage_bytes[BNP_NARR] = {0, 0, 0, 0, 0};
@@ -90,6 +94,8 @@ int launch_T(DevCtx& c, const BnpProgram& p, int pidx, cudaStream_t st, u64* con
     a.scratch = c.scratch;
     a.n = (u32)n;
     a.stride = (u32)stride;
+    a.counter = c.counters + (c.next_counter++ % BNP_NCOUNTERS);
+    CK(cudaMemsetAsync(a.counter, 0, sizeof(u32), st));
     kern<<<(unsigned)blocks, T, smem, st>>>(a);
     CK(cudaGetLastError());
     g_launches++;
@@ -128,6 +134,7 @@ int init_device(int dev) {
     CK(cudaGetDeviceProperties(&prop, dev));
     c.sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    CK(cudaMalloc(&c.counters, BNP_NCOUNTERS * sizeof(u32)));
     if (BNP_NCONST > BNP_MAX_CONST) return BNP_EUNSUPPORTED;
     CK(cudaMemcpyToSymbol(BNP_CONSTS, BNP_CONST_TABLE, (size_t)BNP_NCONST * 64));
     c.d_prog.resize(BNP_NPROG, nullptr);
@@ -279,6 +286,7 @@ void bnp_shutdown(void) {
         for (auto p : c.d_prog)
             if (p) cudaFree(p);
         if (c.scratch) cudaFree(c.scratch);
+        if (c.counters) cudaFree(c.counters);
         for (int i = 0; i < BNP_NARR; i++)
             if (c.stage[i]) cudaFree(c.stage[i]);
         cudaStreamDestroy(c.stream);

@@ -23,6 +23,7 @@ struct VmArgs {
     uint4* scratch;         // [n_scratch][4][total_threads] uint4
     u32 n;                  // elements to process
     u32 stride;             // elements per limb row of the arrays (>= n)
+    u32* counter;           // work counter (zeroed before launch): warps claim 32-element chunks
 };
 
 __device__ __constant__ u32 BNP_CONSTS[BNP_MAX_CONST][16];
@@ -80,8 +81,17 @@ __global__ void __launch_bounds__(T) bnp_vm_kernel(VmArgs args) {
     uint4* scr = args.scratch + gtid;
     const u32 n = args.n, stride = args.stride;
 
-    for (u32 base = blockIdx.x * T; base < n; base += total) {
-        const u32 e_raw = base + threadIdx.x;
+    // Persistent warps: each warp claims the next chunk of 32 elements when it finishes one.  A pairing
+    // is ~10 ms of warp time and a 2^16 batch is only ~2 chunks per resident warp, so a static
+    // grid-stride split would leave the last round badly unbalanced.
+    const u32 lane = threadIdx.x & 31u;
+    for (;;) {
+        u32 chunk = 0;
+        if (lane == 0) chunk = atomicAdd(args.counter, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        const u32 base = chunk * 32u;
+        if (base >= n) break;
+        const u32 e_raw = base + lane;
         const bool active = e_raw < n;
         const u32 e = active ? e_raw : n - 1;  // idle lanes shadow the last element and never store
         const u64* pc = args.prog;

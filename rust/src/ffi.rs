@@ -1,0 +1,23 @@
+//! Hand-written `extern "C"` declarations for ../include/bnp.h (no bindgen-generated dispatch layer).
+#![allow(non_camel_case_types)]
+use core::ffi::{c_char, c_int, c_void};
+
+pub const BNP_VARIANT_REFERENCE: c_int = 0;
+pub const BNP_VARIANT_ARK: c_int = 1;
+
+extern "C" {
+    pub fn bnp_init(devices: *const c_int, n_devices: c_int) -> c_int;
+    pub fn bnp_shutdown();
+    pub fn bnp_strerror(code: c_int) -> *const c_char;
+    pub fn bnp_last_error() -> *const c_char;
+    pub fn bnp_miller_loop_batch(g1: *const u64, g2: *const u64, out: *mut u64, n: usize) -> c_int;
+    pub fn bnp_multi_miller_loop_batch(g1: *const u64, g2: *const u64, out: *mut u64, n: usize, k: c_int) -> c_int;
+    pub fn bnp_final_exp_batch(input: *const u64, out: *mut u64, n: usize, variant: c_int) -> c_int;
+    pub fn bnp_pairing_batch(g1: *const u64, g2: *const u64, out: *mut u64, n: usize, variant: c_int) -> c_int;
+    pub fn bnp_multi_pairing_batch(g1: *const u64, g2: *const u64, out: *mut u64, n: usize, k: c_int, variant: c_int) -> c_int;
+    pub fn bnp_pairing_product(g1: *const u64, g2: *const u64, out: *mut u64, n: usize, variant: c_int) -> c_int;
+    pub fn bnp_frobenius_batch(input: *const u64, out: *mut u64, n: usize, power: usize) -> c_int;
+    pub fn bnp_fq12_mul_batch(a: *const u64, b: *const u64, out: *mut u64, n: usize) -> c_int;
+    pub fn bnp_pairing_dev(device: c_int, stream: *mut c_void, g1: *const u64, g2: *const u64, out: *mut u64,
+                           n: usize, k: c_int, variant: c_int) -> c_int;
+}

@@ -1,0 +1,199 @@
+//! Drop-in for the native path of qope/plonky2-bn254-pairing: same names, same ark-bn254 signatures,
+//! plus the batched slice variants; all arithmetic happens in libbnp (CUDA, sm_100a).
+//!
+//!   miller_loop_native        <- src/miller_loop_native.rs:320
+//!   multi_miller_loop_native  <- src/miller_loop_native.rs:324
+//!   final_exp_native          <- src/final_exp_native.rs:209
+//!   frobenius_map_native      <- src/final_exp_native.rs:17
+//!   pairing                   <- src/pairing.rs:20
+//!
+//! Marshalling: ark's `Fq` is `Fp(BigInt<4>([u64; 4]), _)` in Montgomery form with R = 2^256 - exactly the
+//! limbs libbnp consumes - so it is a limb copy into structure-of-arrays buffers `[K][4][n]`, no conversion.
+//! Rust structs are `repr(Rust)`: they are never passed by pointer, limbs are copied field by field.
+//! Errors: the reference panics (assert!/unwrap); these wrappers panic with libbnp's message.
+mod ffi;
+
+use ark_bn254::{Fq, Fq12, Fq2, G1Affine, G2Affine};
+use ark_ff::{BigInt, Fp};
+use plonky2_bn254::fields::native::MyFq12;
+use std::ffi::CStr;
+
+pub const BN_X: u64 = 4965661367192848881; // final_exp_native.rs:15
+pub const SIX_U_PLUS_2_NAF: [i8; 65] = [
+    0, 0, 0, 1, 0, 1, 0, -1, 0, 0, 1, -1, 0, 0, 1, 0, 0, 1, 1, 0, -1, 0, 0, 1, 0, -1, 0, 0, 0, 0, 1, 1, 1, 0, 0, -1, 0, 0,
+    1, 0, 0, 0, 0, 0, -1, 0, 0, 1, 1, 0, 0, -1, 0, 0, 0, 1, 1, 0, -1, 0, 0, 1, 0, 1, 1,
+]; // miller_loop_native.rs:314
+
+fn check(rc: i32) {
+    if rc != 0 {
+        let (a, b) = unsafe {
+            (CStr::from_ptr(ffi::bnp_strerror(rc)).to_string_lossy().into_owned(),
+             CStr::from_ptr(ffi::bnp_last_error()).to_string_lossy().into_owned())
+        };
+        panic!("libbnp: {a} ({rc}) {b}");
+    }
+}
+
+fn init() {
+    use std::sync::Once;
+    static ONCE: Once = Once::new();
+    ONCE.call_once(|| check(unsafe { ffi::bnp_init(core::ptr::null(), 0) }));
+}
+
+#[inline]
+fn put(buf: &mut [u64], k: usize, n: usize, e: usize, v: &Fq) {
+    for j in 0..4 {
+        buf[(k * 4 + j) * n + e] = (v.0).0[j];
+    }
+}
+#[inline]
+fn get(buf: &[u64], k: usize, n: usize, e: usize) -> Fq {
+    let mut l = [0u64; 4];
+    for j in 0..4 {
+        l[j] = buf[(k * 4 + j) * n + e];
+    }
+    Fp::new_unchecked(BigInt(l)) // already Montgomery, canonical
+}
+
+fn pack_g1(ps: &[G1Affine]) -> Vec<u64> {
+    let n = ps.len();
+    let mut b = vec![0u64; 8 * n];
+    for (e, p) in ps.iter().enumerate() {
+        put(&mut b, 0, n, e, &p.x);
+        put(&mut b, 1, n, e, &p.y);
+    }
+    b
+}
+fn pack_g2(qs: &[G2Affine]) -> Vec<u64> {
+    let n = qs.len();
+    let mut b = vec![0u64; 16 * n];
+    for (e, q) in qs.iter().enumerate() {
+        put(&mut b, 0, n, e, &q.x.c0);
+        put(&mut b, 1, n, e, &q.x.c1);
+        put(&mut b, 2, n, e, &q.y.c0);
+        put(&mut b, 3, n, e, &q.y.c1);
+    }
+    b
+}
+fn pack_fq12(fs: &[MyFq12]) -> Vec<u64> {
+    let n = fs.len();
+    let mut b = vec![0u64; 48 * n];
+    for (e, f) in fs.iter().enumerate() {
+        for k in 0..12 {
+            put(&mut b, k, n, e, &f.coeffs[k]);
+        }
+    }
+    b
+}
+fn unpack_fq12(b: &[u64], n: usize) -> Vec<MyFq12> {
+    (0..n)
+        .map(|e| MyFq12 { coeffs: core::array::from_fn(|k| get(b, k, n, e)) })
+        .collect()
+}
+
+// ---- batched slice variants ----------------------------------------------------------------
+pub fn miller_loop_native_batch(qs: &[G2Affine], ps: &[G1Affine]) -> Vec<MyFq12> {
+    assert_eq!(qs.len(), ps.len());
+    init();
+    let n = ps.len();
+    let (g1, g2) = (pack_g1(ps), pack_g2(qs));
+    let mut out = vec![0u64; 48 * n];
+    check(unsafe { ffi::bnp_miller_loop_batch(g1.as_ptr(), g2.as_ptr(), out.as_mut_ptr(), n) });
+    unpack_fq12(&out, n)
+}
+
+pub fn final_exp_native_batch(fs: &[MyFq12]) -> Vec<MyFq12> {
+    init();
+    let n = fs.len();
+    let inp = pack_fq12(fs);
+    let mut out = vec![0u64; 48 * n];
+    check(unsafe { ffi::bnp_final_exp_batch(inp.as_ptr(), out.as_mut_ptr(), n, ffi::BNP_VARIANT_REFERENCE) });
+    unpack_fq12(&out, n)
+}
+
+pub fn pairing_batch(ps: &[G1Affine], qs: &[G2Affine]) -> Vec<Fq12> {
+    assert_eq!(qs.len(), ps.len());
+    init();
+    let n = ps.len();
+    let (g1, g2) = (pack_g1(ps), pack_g2(qs));
+    let mut out = vec![0u64; 48 * n];
+    check(unsafe { ffi::bnp_pairing_batch(g1.as_ptr(), g2.as_ptr(), out.as_mut_ptr(), n, ffi::BNP_VARIANT_REFERENCE) });
+    unpack_fq12(&out, n).into_iter().map(Into::into).collect() // MyFq12 -> Fq12, as pairing.rs:21
+}
+
+/// `K`-way products (Groth16-verify shape): one Fq12 per group of K pairs, K <= 4.
+pub fn multi_pairing_batch<const K: usize>(groups: &[[(G1Affine, G2Affine); K]]) -> Vec<Fq12> {
+    init();
+    let n = groups.len();
+    let mut g1 = vec![0u64; 8 * K * n];
+    let mut g2 = vec![0u64; 16 * K * n];
+    for (e, g) in groups.iter().enumerate() {
+        for (j, (p, q)) in g.iter().enumerate() {
+            put(&mut g1, 2 * j, n, e, &p.x);
+            put(&mut g1, 2 * j + 1, n, e, &p.y);
+            put(&mut g2, 4 * j, n, e, &q.x.c0);
+            put(&mut g2, 4 * j + 1, n, e, &q.x.c1);
+            put(&mut g2, 4 * j + 2, n, e, &q.y.c0);
+            put(&mut g2, 4 * j + 3, n, e, &q.y.c1);
+        }
+    }
+    let mut out = vec![0u64; 48 * n];
+    check(unsafe {
+        ffi::bnp_multi_pairing_batch(g1.as_ptr(), g2.as_ptr(), out.as_mut_ptr(), n, K as i32, ffi::BNP_VARIANT_REFERENCE)
+    });
+    unpack_fq12(&out, n).into_iter().map(Into::into).collect()
+}
+
+// ---- the reference's scalar signatures -------------------------------------------------------
+#[allow(non_snake_case)]
+pub fn miller_loop_native(Q: &G2Affine, P: &G1Affine) -> MyFq12 {
+    miller_loop_native_batch(core::slice::from_ref(Q), core::slice::from_ref(P)).remove(0)
+}
+
+pub fn multi_miller_loop_native(pairs: Vec<(&G1Affine, &G2Affine)>) -> MyFq12 {
+    // k <= 4: one shared-squaring launch; larger k: product of single loops (equal by miller_loop_native.rs:336-348)
+    let ps: Vec<G1Affine> = pairs.iter().map(|p| *p.0).collect();
+    let qs: Vec<G2Affine> = pairs.iter().map(|p| *p.1).collect();
+    if pairs.len() <= 4 {
+        init();
+        let k = pairs.len();
+        let (mut g1, mut g2) = (vec![0u64; 8 * k], vec![0u64; 16 * k]);
+        for j in 0..k {
+            put(&mut g1, 2 * j, 1, 0, &ps[j].x);
+            put(&mut g1, 2 * j + 1, 1, 0, &ps[j].y);
+            put(&mut g2, 4 * j, 1, 0, &qs[j].x.c0);
+            put(&mut g2, 4 * j + 1, 1, 0, &qs[j].x.c1);
+            put(&mut g2, 4 * j + 2, 1, 0, &qs[j].y.c0);
+            put(&mut g2, 4 * j + 3, 1, 0, &qs[j].y.c1);
+        }
+        let mut out = vec![0u64; 48];
+        check(unsafe { ffi::bnp_multi_miller_loop_batch(g1.as_ptr(), g2.as_ptr(), out.as_mut_ptr(), 1, k as i32) });
+        unpack_fq12(&out, 1).remove(0)
+    } else {
+        miller_loop_native_batch(&qs, &ps).into_iter().reduce(|a, b| a * b).unwrap()
+    }
+}
+
+pub fn final_exp_native(a: MyFq12) -> MyFq12 {
+    final_exp_native_batch(core::slice::from_ref(&a)).remove(0)
+}
+
+pub fn frobenius_map_native(a: MyFq12, power: usize) -> MyFq12 {
+    init();
+    let inp = pack_fq12(core::slice::from_ref(&a));
+    let mut out = vec![0u64; 48];
+    check(unsafe { ffi::bnp_frobenius_batch(inp.as_ptr(), out.as_mut_ptr(), 1, power) });
+    unpack_fq12(&out, 1).remove(0)
+}
+
+pub fn pairing(p: G1Affine, q: G2Affine) -> Fq12 {
+    pairing_batch(&[p], &[q]).remove(0)
+}
+
+// conjugate_fp2 / neg_conjugate_fp2 (miller_loop_native.rs:284-296) are two field negations: kept on the CPU.
+pub fn conjugate_fp2(x: Fq2) -> Fq2 {
+    Fq2::new(x.c0, -x.c1)
+}
+pub fn neg_conjugate_fp2(x: Fq2) -> Fq2 {
+    Fq2::new(-x.c0, x.c1)
+}

@@ -16,6 +16,10 @@ from plonky2_bn254_pairing_b200 import native  # noqa: E402
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 18
     lib = native.init([0])
+    if os.environ.get("BNP_LIB_VARIANT"):
+        lib = native.load(os.environ["BNP_LIB_VARIANT"])
+        dev0 = (ctypes.c_int * 1)(0)
+        native.check(lib.bnp_init(dev0, 1), lib)
     rs = np.random.RandomState(1)
     f = rs.randint(0, 1 << 62, size=(12, 4, n)).astype(np.uint64)
     f[:, 3, :] &= np.uint64((1 << 60) - 1)
@@ -23,9 +27,9 @@ def main():
     d_out = torch.zeros((12, 4, n), dtype=torch.int64, device="cuda")
     stream = torch.cuda.Stream()
     res = {}
-    for T in (64, 128):
+    for T in (32, 64, 128):
         native.check(lib.bnp_set_launch_config(T, 0))
-        for op in ("mul", "sqr", "mulfp", "add", "sub", "dbl", "neg", "mulxi"):
+        for op in os.environ.get("OPS", "mul sqr mulfp add sub dbl neg mulxi").split():
             prog = ("opbench_" + op).encode()
             best = None
             for rep in range(3):
