@@ -8,9 +8,12 @@ struct Fp2 {
     u32 c1[8];
 };
 
-__device__ __forceinline__ void fp2_mul(Fp2& r, const Fp2& a, const Fp2& b) {
+// Operands may be LAZY sums (each component < 2p, as produced by fp2_add_lazy / fp2_sub_lazy) when
+// `lazy` is set: then a0+a1 < 4p < 2^256, every product < 16p^2 < 2^512, a0b0 - a1b1 (+ p*2^256) stays in
+// [0, p*2^256), and a0b1 + a1b0 < 8p^2, whose reduction is < 2.51p and needs a second conditional subtraction.
+__device__ __forceinline__ void fp2_mul(Fp2& r, const Fp2& a, const Fp2& b, bool lazy = false) {
     u32 sa[8], sb[8];
-    add8(sa, a.c0, a.c1);  // < 2p < 2^255
+    add8(sa, a.c0, a.c1);  // < 2p < 2^255 (lazy: < 4p < 2^256)
     add8(sb, b.c0, b.c1);
     u32 P0[16], P1[16], P2[16];
     fp_mul_wide(P0, a.c0, b.c0);
@@ -22,6 +25,34 @@ __device__ __forceinline__ void fp2_mul(Fp2& r, const Fp2& a, const Fp2& b) {
     add_p_masked(P0 + 8, borrow);  // a0b0 - a1b1 (+ p*2^256 when negative) in [0, p*2^256)
     fp_redc(r.c0, P0);
     fp_redc(r.c1, P2);
+    if (lazy) fp_cond_sub_p(r.c1);
+}
+
+// lazy pre-additions for MUL / SQR operands: results in [0, 2p), no reduction
+__device__ __forceinline__ void fp2_add_lazy(Fp2& r, const Fp2& a, const Fp2& b) {
+    add8(r.c0, a.c0, b.c0);
+    add8(r.c1, a.c1, b.c1);
+}
+
+__device__ __forceinline__ void fp_sub_lazy(u32* r, const u32* a, const u32* b) {
+    // (a - b) mod 2^256 + p: equals a - b + p in (0, 2p) whether or not the subtraction wrapped
+    u32 t[8];
+    sub8(t, a, b);
+    asm("add.cc.u32  %0, %8,  " BNP_STR(BNP_P0) ";\n\t"
+        "addc.cc.u32 %1, %9,  " BNP_STR(BNP_P1) ";\n\t"
+        "addc.cc.u32 %2, %10, " BNP_STR(BNP_P2) ";\n\t"
+        "addc.cc.u32 %3, %11, " BNP_STR(BNP_P3) ";\n\t"
+        "addc.cc.u32 %4, %12, " BNP_STR(BNP_P4) ";\n\t"
+        "addc.cc.u32 %5, %13, " BNP_STR(BNP_P5) ";\n\t"
+        "addc.cc.u32 %6, %14, " BNP_STR(BNP_P6) ";\n\t"
+        "addc.u32    %7, %15, " BNP_STR(BNP_P7) ";"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]));
+}
+
+__device__ __forceinline__ void fp2_sub_lazy(Fp2& r, const Fp2& a, const Fp2& b) {
+    fp_sub_lazy(r.c0, a.c0, b.c0);
+    fp_sub_lazy(r.c1, a.c1, b.c1);
 }
 
 __device__ __forceinline__ void fp2_sqr(Fp2& r, const Fp2& a) {
@@ -177,4 +208,86 @@ __device__ __forceinline__ void fp2_inv(Fp2& r, const Fp2& a) {
     fp_mul(r.c0, a.c0, ni);
     fp_mul(m1, a.c1, ni);
     fp_neg(r.c1, m1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// LIN: lazily accumulated linear combinations.  Accumulators are 9-limb two's-complement integers.
+// ---------------------------------------------------------------------------------------------
+
+// a (9 limbs, signed) += neg ? -t : t, t = 9-limb non-negative value
+__device__ __forceinline__ void acc9_addsub(u32* a, const u32* t, u32 neg) {
+    const u32 mask = 0u - neg;
+    u32 junk;
+    asm("add.cc.u32  %9, %19, 0xffffffff;\n\t"   // carry = neg
+        "addc.cc.u32 %0, %0, %10;\n\t"
+        "addc.cc.u32 %1, %1, %11;\n\t"
+        "addc.cc.u32 %2, %2, %12;\n\t"
+        "addc.cc.u32 %3, %3, %13;\n\t"
+        "addc.cc.u32 %4, %4, %14;\n\t"
+        "addc.cc.u32 %5, %5, %15;\n\t"
+        "addc.cc.u32 %6, %6, %16;\n\t"
+        "addc.cc.u32 %7, %7, %17;\n\t"
+        "addc.u32    %8, %8, %18;"
+        : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]),
+          "=&r"(junk)
+        : "r"(t[0] ^ mask), "r"(t[1] ^ mask), "r"(t[2] ^ mask), "r"(t[3] ^ mask), "r"(t[4] ^ mask), "r"(t[5] ^ mask),
+          "r"(t[6] ^ mask), "r"(t[7] ^ mask), "r"(t[8] ^ mask), "r"(neg));
+}
+
+// t (9 limbs) = m * x, m < 2^10, x 8 limbs
+__device__ __forceinline__ void mul_small9(u32* t, u32 m, const u32* x) {
+    u32 E[8], O[8];
+    chain_fresh<0>(E, m, x[0], x[2], x[4], x[6]);
+    chain_fresh<0>(O, m, x[1], x[3], x[5], x[7]);
+    t[0] = E[0];
+    asm("add.cc.u32  %0, %8,  %15;\n\t"
+        "addc.cc.u32 %1, %9,  %16;\n\t"
+        "addc.cc.u32 %2, %10, %17;\n\t"
+        "addc.cc.u32 %3, %11, %18;\n\t"
+        "addc.cc.u32 %4, %12, %19;\n\t"
+        "addc.cc.u32 %5, %13, %20;\n\t"
+        "addc.cc.u32 %6, %14, %21;\n\t"
+        "addc.u32    %7, %22, 0;"
+        : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8])
+        : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(O[0]), "r"(O[1]),
+          "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]));
+}
+
+// one Fq component of one term: acc += m * x (m signed, |m| <= 31)
+__device__ __forceinline__ void acc9_term(u32* acc, int m, const u32* x) {
+    const u32 neg = m < 0 ? 1u : 0u;
+    const u32 am = (u32)(m < 0 ? -m : m);
+    u32 t[9];
+    if (am == 1u) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) t[i] = x[i];
+        t[8] = 0u;
+    } else {
+        mul_small9(t, am, x);
+    }
+    acc9_addsub(acc, t, neg);
+}
+
+// t = 9 * a for a signed 9-limb a (two's complement shift-and-add; |a| < 2^270 so nothing overflows)
+__device__ __forceinline__ void acc9_times9(u32* t, const u32* a) {
+    u32 s[9];
+    s[0] = a[0] << 3;
+#pragma unroll
+    for (int i = 1; i < 9; i++) s[i] = __funnelshift_l(a[i - 1], a[i], 3);
+#pragma unroll
+    for (int i = 0; i < 9; i++) t[i] = a[i];
+    acc9_addsub(t, s, 0u);
+}
+
+// v (9 limbs, 0 <= v < 1024 p) -> canonical residue.  Quotient estimate from the top 32 bits:
+// h = floor(v / 2^232), D = ceil(p / 2^232) = 3171407, q = floor(h / D) is floor(v/p) or one less.
+__device__ __forceinline__ void fp_reduce_lazy(u32* r, const u32* v) {
+    const u32 h = (v[8] << 24) | (v[7] >> 8);
+    const u32 q = h / 3171407u;
+    u32 qp[9];
+    const u32 pp[8] = {(u32)BNP_P0, (u32)BNP_P1, (u32)BNP_P2, (u32)BNP_P3,
+                       (u32)BNP_P4, (u32)BNP_P5, (u32)BNP_P6, (u32)BNP_P7};
+    mul_small9(qp, q, pp);
+    sub8(r, v, qp);  // v - q p < 2p < 2^255: the low 8 limbs are the whole value
+    fp_cond_sub_p(r);
 }

@@ -71,6 +71,59 @@ __device__ __forceinline__ void stg_fp(u64* arr, u32 f, u32 n, u32 e, const u32*
     for (int j = 0; j < 4; j++) p[(size_t)j * n] = (u64)r[2 * j] | ((u64)r[2 * j + 1] << 32);
 }
 
+// K * p for K = 0 .. BNP_LIN_MAX_K (9 limbs each): the offset that makes a LIN accumulator non-negative
+__device__ __constant__ u32 BNP_KP[BNP_LIN_MAX_K + 1][9];
+
+// LIN: d = sum_i diag(m0,m1) x_i + xi * sum_j diag(m0,m1) x_j, accumulated lazily, reduced once.
+// `pc` points at the first term word; returns the advanced pointer.
+template <int T>
+__device__ __forceinline__ const u64* vm_lin(const Slots<T>& S, const u64* pc, u32 d, u32 nterms, u32 K) {
+    u32 A0[9], A1[9], X0[9], X1[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) A0[i] = A1[i] = X0[i] = X1[i] = 0u;
+    bool any_xi = false;
+    u64 w = 0;
+#pragma unroll 1
+    for (u32 j = 0; j < nterms; j++) {
+        if ((j & 1u) == 0u) w = __ldg(pc++);
+        const u32 t = (j & 1u) ? (u32)(w >> 32) : (u32)w;
+        const u32 slot = t & 0xffu;
+        const bool xi = (t >> 8) & BNP_LIN_XI;
+        const int m0 = (int)(signed char)((t >> 16) & 0xffu);
+        const int m1 = (int)(signed char)(t >> 24);
+        Fp2 x;
+        S.load(x, slot);
+        if (xi) {
+            any_xi = true;
+            if (m0) acc9_term(X0, m0, x.c0);
+            if (m1) acc9_term(X1, m1, x.c1);
+        } else {
+            if (m0) acc9_term(A0, m0, x.c0);
+            if (m1) acc9_term(A1, m1, x.c1);
+        }
+    }
+    if (any_xi) {
+        // (A0, A1) += xi * (X0, X1) = (9 X0 - X1, X0 + 9 X1)
+        u32 n0[9], n1[9];
+        acc9_times9(n0, X0);
+        acc9_times9(n1, X1);
+        acc9_addsub(A0, n0, 0u);
+        acc9_addsub(A0, X1, 1u);
+        acc9_addsub(A1, X0, 0u);
+        acc9_addsub(A1, n1, 0u);
+    }
+    u32 kp[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) kp[i] = BNP_KP[K][i];
+    acc9_addsub(A0, kp, 0u);
+    acc9_addsub(A1, kp, 0u);
+    Fp2 r;
+    fp_reduce_lazy(r.c0, A0);
+    fp_reduce_lazy(r.c1, A1);
+    S.store(d, r);
+    return pc;
+}
+
 template <int T>
 __global__ void __launch_bounds__(T) bnp_vm_kernel(VmArgs args) {
     extern __shared__ uint4 bnp_smem[];
@@ -95,22 +148,44 @@ __global__ void __launch_bounds__(T) bnp_vm_kernel(VmArgs args) {
         const bool active = e_raw < n;
         const u32 e = active ? e_raw : n - 1;  // idle lanes shadow the last element and never store
         const u64* pc = args.prog;
-        u64 ins = __ldg(pc);
+        u64 ins = __ldg(pc++);
         for (;;) {
-            const u64 nxt = __ldg(++pc);  // prefetch (every program ends with END followed by padding)
             const u32 lo = (u32)ins, hi = (u32)(ins >> 32);
-            const u32 op = lo & 0xffu, d = (lo >> 8) & 0xfffu, a = lo >> 20, b = hi & 0xfffu, imm = hi >> 12;
+            const u32 op = lo & 0xffu, d = (lo >> 8) & 0xffu, a = (lo >> 16) & 0xffu, b = lo >> 24;
+            const u32 c = hi & 0xffu, ee = (hi >> 8) & 0xffu, imm = hi >> 16;
             if (op == BNP_OP_END) break;
+            if (op == BNP_OP_LIN) {
+                pc = vm_lin<T>(S, pc, d, a, imm);
+                ins = __ldg(pc++);
+                continue;
+            }
+            const u64 nxt = __ldg(pc++);  // prefetch (every program ends with END followed by padding)
             Fp2 x, y, r;
             switch (op) {
-                case BNP_OP_MUL:
+                case BNP_OP_MUL: {
                     S.load(x, a);
-                    S.load(y, b);
-                    fp2_mul(r, x, y);
+                    S.load(y, c);
+                    if (imm) {  // Karatsuba operands: (a +- b) * (c +- e), sums kept lazy (< 2p)
+                        Fp2 t;
+                        if (imm & BNP_MUL_B) {
+                            S.load(t, b);
+                            if (imm & BNP_MUL_BNEG) fp2_sub_lazy(x, x, t); else fp2_add_lazy(x, x, t);
+                        }
+                        if (imm & BNP_MUL_E) {
+                            S.load(t, ee);
+                            if (imm & BNP_MUL_ENEG) fp2_sub_lazy(y, y, t); else fp2_add_lazy(y, y, t);
+                        }
+                    }
+                    fp2_mul(r, x, y, imm != 0);
                     S.store(d, r);
                     break;
+                }
                 case BNP_OP_SQR:
                     S.load(x, a);
+                    if (imm & BNP_MUL_B) {
+                        S.load(y, b);
+                        if (imm & BNP_MUL_BNEG) fp2_sub(x, x, y); else fp2_add(x, x, y);
+                    }
                     fp2_sqr(r, x);
                     S.store(d, r);
                     break;
@@ -122,42 +197,6 @@ __global__ void __launch_bounds__(T) bnp_vm_kernel(VmArgs args) {
                     S.store(d, r);
                     break;
                 }
-                case BNP_OP_ADD:
-                    S.load(x, a);
-                    S.load(y, b);
-                    fp2_add(r, x, y);
-                    S.store(d, r);
-                    break;
-                case BNP_OP_SUB:
-                    S.load(x, a);
-                    S.load(y, b);
-                    fp2_sub(r, x, y);
-                    S.store(d, r);
-                    break;
-                case BNP_OP_DBL:
-                    S.load(x, a);
-                    fp2_add(r, x, x);
-                    S.store(d, r);
-                    break;
-                case BNP_OP_NEG:
-                    S.load(x, a);
-                    fp2_neg(r, x);
-                    S.store(d, r);
-                    break;
-                case BNP_OP_CONJ:
-                    S.load(x, a);
-                    fp2_conj(r, x);
-                    S.store(d, r);
-                    break;
-                case BNP_OP_MULXI:
-                    S.load(x, a);
-                    fp2_mul_xi(r, x);
-                    S.store(d, r);
-                    break;
-                case BNP_OP_MOV:
-                    S.load(x, a);
-                    S.store(d, x);
-                    break;
                 case BNP_OP_LDC:
 #pragma unroll
                     for (int i = 0; i < 8; i++) {

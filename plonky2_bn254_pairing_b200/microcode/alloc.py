@@ -1,4 +1,4 @@
-"""Slot allocation: SSA program -> instruction words over `n_slots` shared-memory slots.
+"""Slot allocation: fused SSA program (fuse.py) -> instruction words over `n_slots` shared-memory slots.
 
 The programs are straight-line, so every value's future uses are known exactly; eviction takes the
 resident value whose next use is furthest away (Belady).  Evicted values go to per-thread scratch in
@@ -40,14 +40,14 @@ def allocate(ops, n_slots):
     loc = {}                      # value -> slot
     slot_val = [None] * n_slots
     free_slots = list(range(n_slots - 1, -1, -1))
-    scratch_of = {}               # value -> scratch index (copy is valid for the value's whole life: SSA)
+    scratch_of = {}               # value -> scratch index (copy stays valid for the value's whole life: SSA)
     free_scratch = []
     n_scratch = 0
     words = []
     stats = defaultdict(int)
 
-    def emit(op, d=0, a=0, b=0, imm=0):
-        words.append(isa.encode(op, d, a, b, imm))
+    def emit(op, **kw):
+        words.append(isa.encode(op, **kw))
         stats[op] += 1
 
     def release(v):
@@ -63,17 +63,16 @@ def allocate(ops, n_slots):
         nonlocal n_scratch
         if free_slots:
             return free_slots.pop()
-        best, best_nu = None, -1
+        best, best_key = None, -1
         for s in range(n_slots):
             v = slot_val[s]
             if v in protect:
                 continue
             nu = next_use(v, i)
-            # prefer victims that need no store (rematerialisable or already in scratch)
-            cheap = defop[v].op in REMAT or v in scratch_of
+            cheap = defop[v].op in REMAT or v in scratch_of  # eviction needs no store
             key = nu * 2 + (1 if cheap else 0)
-            if key > best_nu:
-                best, best_nu = s, key
+            if key > best_key:
+                best, best_key = s, key
         assert best is not None, "not enough slots for one instruction"
         v = slot_val[best]
         if next_use(v, i) != INF and defop[v].op not in REMAT and v not in scratch_of:
@@ -103,31 +102,48 @@ def allocate(ops, n_slots):
         slot_val[s] = v
 
     for i, o in enumerate(ops):
-        if o.op in REMAT and next_use(o.dst, i + 1) == INF:
-            continue  # dead load
         if o.op in REMAT:
-            # defer: materialised at first use (keeps slots free until the value is needed)
-            continue
+            continue  # materialised at first use
         protect = set(o.srcs)
+        assert len(protect) + 1 <= n_slots, "instruction needs more slots than available"
         for v in o.srcs:
             materialise(v, i, protect)
         src_slots = [loc[v] for v in o.srcs]
-        # sources whose last use is this instruction free their slot before the destination is chosen
         for v in set(o.srcs):
             if next_use(v, i + 1) == INF:
-                release(v)
+                release(v)  # last use: the destination may reuse the slot (handlers read before they write)
+        d = 0
         if o.dst is not None:
             d = take_slot(i + 1, protect=set(v for v in o.srcs if v in loc))
             loc[o.dst] = d
             slot_val[d] = o.dst
-        if o.op in ("MUL", "ADD", "SUB"):
-            emit(o.op, d=d, a=src_slots[0], b=src_slots[1])
+        if o.op == "MUL":
+            k = 0
+            a = src_slots[k]; k += 1
+            b = 0
+            if o.flags & isa.MUL_B:
+                b = src_slots[k]; k += 1
+            c = src_slots[k]; k += 1
+            e = 0
+            if o.flags & isa.MUL_E:
+                e = src_slots[k]; k += 1
+            emit("MUL", d=d, a=a, b=b, c=c, e=e, imm=o.flags)
+        elif o.op == "SQR":
+            b = src_slots[1] if o.flags & isa.MUL_B else 0
+            emit("SQR", d=d, a=src_slots[0], b=b, imm=o.flags)
         elif o.op == "MULFP":
-            emit(o.op, d=d, a=src_slots[0], b=src_slots[1], imm=o.imm)
-        elif o.op in ("SQR", "NEG", "CONJ", "MULXI", "MOV", "INV", "DBL"):
-            emit(o.op, d=d, a=src_slots[0])
+            emit("MULFP", d=d, a=src_slots[0], b=src_slots[1], imm=o.imm)
+        elif o.op == "INV":
+            emit("INV", d=d, a=src_slots[0])
         elif o.op == "STG":
             emit("STG", d=o.f_lo, a=src_slots[0], b=o.f_hi, imm=o.imm)
+        elif o.op == "LIN":
+            emit("LIN", d=d, a=len(o.terms), imm=o.K)
+            tw = [isa.encode_term(loc_s, xi, m0, m1) for loc_s, (_, xi, m0, m1) in zip(src_slots, o.terms)]
+            if len(tw) % 2:
+                tw.append(0)
+            for j in range(0, len(tw), 2):
+                words.append(tw[j] | (tw[j + 1] << 32))
         else:
             raise ValueError(o.op)
         if o.dst is not None and next_use(o.dst, i + 1) == INF:

@@ -1,36 +1,42 @@
-"""Instruction set of the Fq2 sequencer kernel (csrc/vm.cu).
+"""Instruction set of the Fq2 sequencer kernel (csrc/vm.cuh).
 
 The GPU kernel is a per-thread register machine whose registers ("slots") are Fq2 values held in
 shared memory; every thread runs the same straight-line program on its own pairing, so control
-flow is uniform across the grid.  One instruction is a 64-bit word:
+flow is uniform across the grid.  One instruction word is 64 bits, eight byte-wide fields:
 
-    bits  0..7   opcode
-    bits  8..19  d   (destination slot, or an Fq index for STG)
-    bits 20..31  a   (source slot,      or an Fq index for LDG)
-    bits 32..43  b   (source slot,      or an Fq index for LDG/STG)
-    bits 44..63  imm (constant index, array id, scratch index, flags)
+    byte 0  opcode
+    byte 1  d     destination slot          (STG: Fq index of the c0 half)
+    byte 2  a     source slot               (LDG: Fq index of the c0 half)
+    byte 3  b     source slot               (LDG/STG: Fq index of the c1 half)
+    byte 4  c     source slot
+    byte 5  e     source slot
+    byte 6-7 imm  16-bit immediate (constant index, array id, scratch index, flags)
+
+MUL / SQR take optional pre-additions (Karatsuba operands are sums of two slots):
+    MUL  d = (a [+-b]) * (c [+-e])     imm bit0: b present, bit1: b subtracted, bit2: e present, bit3: e subtracted
+    SQR  d = (a [+-b])^2               imm bit0: b present, bit1: b subtracted
+LIN is the only linear opcode: a variable-length instruction
+    d = sum_i diag(m0_i, m1_i) * x_i  +  xi * sum_j diag(m0_j, m1_j) * x_j        (xi = 9 + u)
+with small signed integer multipliers per Fq component (this subsumes add, sub, neg, double, conj,
+multiplication by xi and by small constants).  Header word: d, a = number of terms, imm = K (the
+multiple of p that makes the lazily accumulated value non-negative); each following word carries
+two 32-bit term descriptors: [slot:8][flags:8][m0:int8][m1:int8], flags bit0 = term belongs to the xi sum.
 
 `emit_c_defines()` writes the opcode numbers into the generated header so the CUDA side cannot drift.
 """
 
 OPS = [
     "END",    # stop
-    "MUL",    # d = a * b                      (Fq2)
-    "SQR",    # d = a^2
+    "MUL",    # d = (a [+-b]) * (c [+-e])
+    "SQR",    # d = (a [+-b])^2
     "MULFP",  # d = a * s, s = c0 (imm=0) or c1 (imm=1) half of slot b, an Fq scalar
-    "ADD",    # d = a + b
-    "SUB",    # d = a - b
-    "NEG",    # d = -a
-    "CONJ",   # d = conj(a) = (a.c0, -a.c1)
-    "MULXI",  # d = a * (9 + u)
-    "MOV",    # d = a
+    "LIN",    # d = linear combination (variable length, see above)
     "LDC",    # d = const[imm]
     "LDG",    # d = (arr[imm][a], arr[imm][b])   two Fq of this thread's element of global array imm
     "STG",    # arr[imm][d], arr[imm][b] = a.c0, a.c1
     "SPILL",  # scratch[imm] = a
     "FILL",   # d = scratch[imm]
     "INV",    # d = 1 / a   (Fq2)
-    "DBL",    # d = a + a
 ]
 OPCODE = {name: i for i, name in enumerate(OPS)}
 
@@ -39,20 +45,42 @@ ARR_G1 = 0    # [2k Fq][n]   (x, y) of each G1 point; k points per element for m
 ARR_G2 = 1    # [4k Fq][n]   (x.c0, x.c1, y.c0, y.c1)
 ARR_F12 = 2   # [12 Fq][n]   MyFq12 input  (coeffs[0..11])
 ARR_OUT = 3   # [12 Fq][n]   MyFq12 output
-ARR_AUX = 4   # second output / input array (program specific)
+ARR_AUX = 4   # second input array (program specific)
 
-FIELD_MAX = 0xFFF
-IMM_MAX = 0xFFFFF
+MUL_B, MUL_BNEG, MUL_E, MUL_ENEG = 1, 2, 4, 8
+LIN_XI = 1
+LIN_MAX_TERMS = 8
+LIN_MAX_MULT = 31
+LIN_MAX_K = 63      # size of the K*p table in the kernel
 
 
-def encode(op, d=0, a=0, b=0, imm=0):
-    assert 0 <= d <= FIELD_MAX and 0 <= a <= FIELD_MAX and 0 <= b <= FIELD_MAX and 0 <= imm <= IMM_MAX
-    return OPCODE[op] | (d << 8) | (a << 20) | (b << 32) | (imm << 44)
+def encode(op, d=0, a=0, b=0, c=0, e=0, imm=0):
+    for v in (d, a, b, c, e):
+        assert 0 <= v <= 0xFF, v
+    assert 0 <= imm <= 0xFFFF
+    return OPCODE[op] | (d << 8) | (a << 16) | (b << 24) | (c << 32) | (e << 40) | (imm << 48)
 
 
 def decode(word):
-    return (OPS[word & 0xFF], (word >> 8) & 0xFFF, (word >> 20) & 0xFFF, (word >> 32) & 0xFFF, (word >> 44) & 0xFFFFF)
+    return (OPS[word & 0xFF], (word >> 8) & 0xFF, (word >> 16) & 0xFF, (word >> 24) & 0xFF, (word >> 32) & 0xFF,
+            (word >> 40) & 0xFF, (word >> 48) & 0xFFFF)
+
+
+def encode_term(slot, xi, m0, m1):
+    assert 0 <= slot <= 0xFF and -LIN_MAX_MULT <= m0 <= LIN_MAX_MULT and -LIN_MAX_MULT <= m1 <= LIN_MAX_MULT
+    return slot | ((LIN_XI if xi else 0) << 8) | ((m0 & 0xFF) << 16) | ((m1 & 0xFF) << 24)
+
+
+def decode_term(t):
+    def s8(v):
+        return v - 256 if v >= 128 else v
+
+    return (t & 0xFF, bool((t >> 8) & LIN_XI), s8((t >> 16) & 0xFF), s8((t >> 24) & 0xFF))
 
 
 def emit_c_defines():
-    return "".join("#define BNP_OP_%s %d\n" % (name, i) for i, name in enumerate(OPS))
+    s = "".join("#define BNP_OP_%s %d\n" % (name, i) for i, name in enumerate(OPS))
+    s += "#define BNP_MUL_B %d\n#define BNP_MUL_BNEG %d\n#define BNP_MUL_E %d\n#define BNP_MUL_ENEG %d\n" % (
+        MUL_B, MUL_BNEG, MUL_E, MUL_ENEG)
+    s += "#define BNP_LIN_XI %d\n#define BNP_LIN_MAX_K %d\n" % (LIN_XI, LIN_MAX_K)
+    return s

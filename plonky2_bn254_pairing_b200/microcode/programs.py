@@ -305,14 +305,26 @@ def prog_fq12_mul(b):
     b.st_fq12(isa.ARR_OUT, b.fq12_mul(b.ld_fq12(isa.ARR_F12), b.ld_fq12(isa.ARR_AUX)))
 
 
+OPTEST_OUTPUTS = 24
+
+
 def prog_optest(b):
-    """One of every arithmetic opcode, for op-level GPU parity tests.  F12 holds 6 input slots; OUT gets
-    MUL, SQR, MULFP(c0), MULFP(c1), ADD, SUB, NEG, CONJ, MULXI, DBL, INV, (a*const) in 12 slots."""
+    """Every opcode and operand form once, for op-level GPU parity tests.  F12 holds 6 input slots x0..x5;
+    OUT gets OPTEST_OUTPUTS slots.  The expected values are spelled out in tests/optest_expect.py."""
     x = b.ld_fq12(isa.ARR_F12)
     outs = [
         x[0] * x[1], x[2].sqr(), x[3].mulfp(x[4], 0), x[3].mulfp(x[4], 1), x[0] + x[5], x[1] - x[2],
         -x[3], x[4].conj(), x[5].mulxi(), x[0].dbl(), x[1].inv(), x[2] * b.const(_C3),
+        (x[0] + x[1]) * (x[2] + x[3]), (x[0] - x[1]) * (x[2] - x[3]), (x[0] + x[1]) * x[2], x[0] * (x[2] - x[3]),
+        (x[4] + x[5]).sqr(), (x[4] - x[5]).sqr(),
+        x[0] - x[1] - x[2] + x[3],
+        x[0] + (x[1] - x[2] - x[3]).mulxi(),
+        b.times(x[0], 27) - x[1].mulxi(),
+        (x[2] - x[3]).dbl() + x[2],
+        x[0].conj() + x[1].mulxi() - x[2].dbl(),
+        b.times(x[5], 12) - x[4].conj(),
     ]
+    assert len(outs) == OPTEST_OUTPUTS
     for i, v in enumerate(outs):
         b.stg(isa.ARR_OUT, 2 * i, 2 * i + 1, v)
 
@@ -339,8 +351,12 @@ def prog_opbench(b, op, count=2048):
             r = -a
         elif op == "MULXI":
             r = a.mulxi()
-        elif op == "LDC":
-            r = b.const((i + 2, 1)) + a  # one LDC + one ADD
+        elif op == "LIN4":
+            r = a - c - vals[(i + 2) % 6] + vals[(i + 3) % 6]
+        elif op == "LIN4XI":
+            r = a + (c - vals[(i + 2) % 6] - vals[(i + 3) % 6]).mulxi()
+        elif op == "MULS":
+            r = (a + c) * (vals[(i + 2) % 6] + vals[(i + 3) % 6])
         else:
             raise ValueError(op)
         vals[i % 6] = r
@@ -357,7 +373,7 @@ PROGRAMS = [
     ("pairing_v1", prog_pairing, {"variant": 1}),
     ("fq12_mul", prog_fq12_mul, {}),
     ("optest", prog_optest, {}),
-] + [("opbench_" + o.lower(), prog_opbench, {"op": o}) for o in ("MUL", "SQR", "MULFP", "ADD", "SUB", "DBL", "NEG", "MULXI")] \
+] + [("opbench_" + o.lower(), prog_opbench, {"op": o}) for o in ("MUL", "SQR", "MULFP", "ADD", "SUB", "DBL", "NEG", "MULXI", "LIN4", "LIN4XI", "MULS")] \
   + [("frobenius_%d" % k, prog_frobenius, {"power": k}) for k in range(12)] \
   + [("miller_x%d" % k, prog_miller, {"n_pairs": k}) for k in (2, 3, 4)] \
   + [("pairing_x%d_v%d" % (k, v), prog_pairing, {"variant": v, "n_pairs": k}) for k in (2, 3, 4) for v in (0, 1)]

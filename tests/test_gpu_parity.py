@@ -32,32 +32,19 @@ def _dev(a):
 def test_every_opcode_against_plain_integer_semantics(lib):
     import torch
 
-    rnd = random.Random(7)
-    edge = [0, 1, 2, O.P - 1, O.P - 2, (O.P - 1) // 2, (O.P + 1) // 2, 9, 2 ** 253, 2 ** 224 - 1]
-    rows = [[rnd.randrange(O.P) for _ in range(12)] for _ in range(96)]
-    for i, v in enumerate(edge):
-        rows[i] = [v] * 12
-        rows[len(edge) + i] = [rnd.choice(edge) for _ in range(12)]
-    for r in rows:  # slot 1 = (r[1], r[7]) is inverted by the program: keep it non-zero
-        if r[1] == 0 and r[7] == 0:
-            r[1] = 5
+    import optest_expect as X
+    from plonky2_bn254_pairing_b200.microcode.programs import OPTEST_OUTPUTS
+
+    rows = X.edge_rows(random.Random(7))
     n = len(rows)
     d_in = _dev(api.pack_soa(rows))
-    d_out = torch.zeros((24, 4, n), dtype=torch.int64, device="cuda")
+    d_out = torch.zeros((2 * OPTEST_OUTPUTS, 4, n), dtype=torch.int64, device="cuda")
     native.check(lib.bnp_run_program_dev(0, None, b"optest", None, None, d_in.data_ptr(), None, d_out.data_ptr(), n))
     torch.cuda.synchronize()
     out = api.unpack_soa(d_out.cpu().numpy().view(np.uint64))  # also asserts every limb is canonical
-    c = O._expected_c()
-    c3 = O.fq2_mul(O.fq2_mul(c, c), c)
-    names = ["MUL", "SQR", "MULFP0", "MULFP1", "ADD", "SUB", "NEG", "CONJ", "MULXI", "DBL", "INV", "MULC"]
     for e in range(n):
-        x = [(rows[e][i], rows[e][i + 6]) for i in range(6)]
-        want = [
-            O.fq2_mul(x[0], x[1]), O.fq2_sqr(x[2]), O.fq2_mul(x[3], (x[4][0], 0)), O.fq2_mul(x[3], (x[4][1], 0)),
-            O.fq2_add(x[0], x[5]), O.fq2_sub(x[1], x[2]), O.fq2_neg(x[3]), O.conjugate_fp2(x[4]),
-            O.fq2_mul(x[5], O.XI), O.fq2_add(x[0], x[0]), O.fq2_inv(x[1]), O.fq2_mul(x[2], c3),
-        ]
-        for i, nm in enumerate(names):
+        want = X.expected(rows[e])
+        for i, nm in enumerate(X.NAMES):
             assert (out[e][2 * i], out[e][2 * i + 1]) == want[i], (e, nm)
 
 

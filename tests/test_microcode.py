@@ -12,17 +12,30 @@ from plonky2_bn254_pairing_b200.microcode.builder import ConstPool, naf_digits
 def run(name, arrays, n_slots):
     pool = ConstPool()
     b = programs.build_program(name, pool)
-    al = alloc.allocate(b.ops, n_slots)
-    for w in al.words:  # every operand field within the slot budget
-        op, d, a, bb, imm = isa.decode(w)
-        if op in ("MUL", "ADD", "SUB", "MULFP"):
+    from plonky2_bn254_pairing_b200.microcode import fuse
+    al = alloc.allocate(fuse.fuse(b.ops), n_slots)
+    pc = 0
+    while pc < len(al.words):  # every operand field within the slot budget
+        op, d, a, bb, c, e, imm = isa.decode(al.words[pc])
+        pc += 1
+        if op == "MUL":
+            assert max(d, a, bb, c, e) < n_slots
+        elif op in ("SQR", "MULFP"):
             assert max(d, a, bb) < n_slots
-        elif op in ("SQR", "NEG", "CONJ", "MULXI", "MOV", "INV", "DBL"):
+        elif op == "INV":
             assert max(d, a) < n_slots
-        elif op in ("SPILL",):
+        elif op == "SPILL":
             assert a < n_slots and imm < max(al.n_scratch, 1)
-        elif op in ("FILL",):
+        elif op == "FILL":
             assert d < n_slots and imm < al.n_scratch
+        elif op == "LIN":
+            assert d < n_slots and 1 <= a <= isa.LIN_MAX_TERMS and imm <= isa.LIN_MAX_K
+            for j in range(a):
+                t = (al.words[pc + j // 2] >> (32 * (j % 2))) & 0xFFFFFFFF
+                assert isa.decode_term(t)[0] < n_slots
+            pc += (a + 1) // 2
+        elif op == "END":
+            break
     arrays = dict(arrays)
     arrays[isa.ARR_OUT] = {}
     interp.run(al.words, pool.values, arrays, al.n_slots, al.n_scratch)
@@ -111,8 +124,44 @@ def test_work_counts_not_above_survey_canonical():
 
 
 def test_encode_decode_roundtrip_and_naf():
-    w = isa.encode("MULFP", d=5, a=1023, b=77, imm=1)
-    assert isa.decode(w) == ("MULFP", 5, 1023, 77, 1)
+    w = isa.encode("MUL", d=5, a=255, b=77, c=3, e=9, imm=isa.MUL_B | isa.MUL_ENEG)
+    assert isa.decode(w) == ("MUL", 5, 255, 77, 3, 9, isa.MUL_B | isa.MUL_ENEG)
+    assert isa.decode_term(isa.encode_term(13, True, -27, 31)) == (13, True, -27, 31)
     assert naf_digits(O.BN_X) == O.get_naf([O.BN_X])[:len(naf_digits(O.BN_X))]
     assert sum(d << i for i, d in enumerate(programs.SIX_U_PLUS_2_NAF)) == 6 * O.BN_X + 2
     assert programs.SIX_U_PLUS_2_NAF == O.SIX_U_PLUS_2_NAF
+
+
+def test_optest_program_matches_expectations():
+    """The op-level GPU test's expected values, checked here against the interpreter (incl. edge values)."""
+    import optest_expect as X
+
+    rows = X.edge_rows(random.Random(7), n_random=24)
+    for r in rows:
+        pool = ConstPool()
+        b = programs.build_program("optest", pool)
+        from plonky2_bn254_pairing_b200.microcode import fuse
+        al = alloc.allocate(fuse.fuse(b.ops), 14)
+        arrays = {isa.ARR_F12: r, isa.ARR_OUT: {}}
+        interp.run(al.words, pool.values, arrays, al.n_slots, al.n_scratch)
+        want = X.expected(r)
+        for i in range(programs.OPTEST_OUTPUTS):
+            assert (arrays[isa.ARR_OUT][2 * i], arrays[isa.ARR_OUT][2 * i + 1]) == want[i], X.NAMES[i]
+
+
+def test_fusion_preserves_results_and_cuts_slot_moves():
+    from plonky2_bn254_pairing_b200.microcode import fuse
+
+    p, q = PTS[3]
+    pool = ConstPool()
+    b = programs.build_program("pairing_v0", pool)
+    res = {}
+    for en in (False, True):
+        al = alloc.allocate(fuse.fuse(b.ops, enable=en), 14)
+        arrays = g1g2([PTS[3]])
+        arrays[isa.ARR_OUT] = {}
+        interp.run(al.words, pool.values, arrays, al.n_slots, al.n_scratch)
+        res[en] = ([arrays[isa.ARR_OUT][i] for i in range(12)], interp.work(al.words))
+    assert res[False][0] == res[True][0] == O.pairing(p, q)
+    assert res[True][1]["macs"] == res[False][1]["macs"]
+    assert res[True][1]["slot_moves"] < 0.7 * res[False][1]["slot_moves"]

@@ -29,7 +29,7 @@ def main():
     res = {}
     for T in (32, 64, 128):
         native.check(lib.bnp_set_launch_config(T, 0))
-        for op in os.environ.get("OPS", "mul sqr mulfp add sub dbl neg mulxi").split():
+        for op in os.environ.get("OPS", "mul sqr mulfp add sub dbl neg mulxi lin4 lin4xi muls").split():
             prog = ("opbench_" + op).encode()
             best = None
             for rep in range(3):
