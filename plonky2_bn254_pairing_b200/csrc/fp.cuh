@@ -42,8 +42,8 @@ __device__ __forceinline__ void chain_fresh(u32* x, u32 s, u32 q0, u32 q1, u32 q
         "mul.lo.u32 %2, %8, %10; mul.hi.u32 %3, %8, %10;\n\t"
         "mul.lo.u32 %4, %8, %11; mul.hi.u32 %5, %8, %11;\n\t"
         "mul.lo.u32 %6, %8, %12; mul.hi.u32 %7, %8, %12;"
-        : "=r"(x[B]), "=r"(x[B + 1]), "=r"(x[B + 2]), "=r"(x[B + 3]), "=r"(x[B + 4]), "=r"(x[B + 5]),
-          "=r"(x[B + 6]), "=r"(x[B + 7])
+        : "=&r"(x[B]), "=&r"(x[B + 1]), "=&r"(x[B + 2]), "=&r"(x[B + 3]), "=&r"(x[B + 4]), "=&r"(x[B + 5]),
+          "=&r"(x[B + 6]), "=&r"(x[B + 7])
         : "r"(s), "r"(q0), "r"(q1), "r"(q2), "r"(q3));
 }
 
@@ -55,7 +55,7 @@ __device__ __forceinline__ void chain_top2(u32* x, u32 s, u32 q0, u32 q1, u32 q2
         "madc.lo.cc.u32 %4, %8, %11, %4; madc.hi.cc.u32 %5, %8, %11, %5;\n\t"
         "madc.lo.cc.u32 %6, %8, %12, 0;  madc.hi.u32    %7, %8, %12, 0;"
         : "+r"(x[B]), "+r"(x[B + 1]), "+r"(x[B + 2]), "+r"(x[B + 3]), "+r"(x[B + 4]), "+r"(x[B + 5]),
-          "=r"(x[B + 6]), "=r"(x[B + 7])
+          "=&r"(x[B + 6]), "=&r"(x[B + 7])
         : "r"(s), "r"(q0), "r"(q1), "r"(q2), "r"(q3));
 }
 
@@ -67,7 +67,7 @@ __device__ __forceinline__ void chain_top1(u32* x, u32 s, u32 q0, u32 q1, u32 q2
         "madc.lo.cc.u32 %4, %8, %11, %4; madc.hi.cc.u32 %5, %8, %11, %5;\n\t"
         "madc.lo.cc.u32 %6, %8, %12, %6; madc.hi.u32    %7, %8, %12, 0;"
         : "+r"(x[B]), "+r"(x[B + 1]), "+r"(x[B + 2]), "+r"(x[B + 3]), "+r"(x[B + 4]), "+r"(x[B + 5]),
-          "+r"(x[B + 6]), "=r"(x[B + 7])
+          "+r"(x[B + 6]), "=&r"(x[B + 7])
         : "r"(s), "r"(q0), "r"(q1), "r"(q2), "r"(q3));
 }
 
@@ -80,7 +80,7 @@ __device__ __forceinline__ void chain_full(u32* x, u32 s, u32 q0, u32 q1, u32 q2
         "madc.lo.cc.u32 %6, %9, %13, %6; madc.hi.cc.u32 %7, %9, %13, %7;\n\t"
         "addc.u32 %8, 0, 0;"
         : "+r"(x[B]), "+r"(x[B + 1]), "+r"(x[B + 2]), "+r"(x[B + 3]), "+r"(x[B + 4]), "+r"(x[B + 5]),
-          "+r"(x[B + 6]), "+r"(x[B + 7]), "=r"(x[B + 8])
+          "+r"(x[B + 6]), "+r"(x[B + 7]), "=&r"(x[B + 8])
         : "r"(s), "r"(q0), "r"(q1), "r"(q2), "r"(q3));
 }
 
@@ -130,8 +130,8 @@ __device__ __forceinline__ void fp_mul_wide(u32* r /*16*/, const u32* a /*8*/, c
         "addc.cc.u32 %12, %27, %42;\n\t"
         "addc.cc.u32 %13, %28, %43;\n\t"
         "addc.u32    %14, %29, %44;"
-        : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(r[8]),
+          "=&r"(r[9]), "=&r"(r[10]), "=&r"(r[11]), "=&r"(r[12]), "=&r"(r[13]), "=&r"(r[14]), "=&r"(r[15])
         : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]),
           "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]), "r"(O[0]), "r"(O[1]),
           "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]), "r"(O[9]), "r"(O[10]),
@@ -158,8 +158,8 @@ __device__ __forceinline__ void redc_row0(u32* E, u32* O) {
         "madc.lo.cc.u32 %6,  %17, " BNP_STR(BNP_P6) ", %6; madc.hi.cc.u32 %7, %17, " BNP_STR(BNP_P6) ", %7;\n\t"
         "addc.u32 %8, 0, 0;"
         : "+r"(E[0]), "+r"(E[1]), "+r"(E[2]), "+r"(E[3]), "+r"(E[4]), "+r"(E[5]), "+r"(E[6]), "+r"(E[7]),
-          "=r"(E[8]), "=r"(O[0]), "=r"(O[1]), "=r"(O[2]), "=r"(O[3]), "=r"(O[4]), "=r"(O[5]), "=r"(O[6]),
-          "=r"(O[7]), "=&r"(m), "=r"(junk));
+          "=&r"(E[8]), "=&r"(O[0]), "=&r"(O[1]), "=&r"(O[2]), "=&r"(O[3]), "=&r"(O[4]), "=&r"(O[5]), "=&r"(O[6]),
+          "=&r"(O[7]), "=&r"(m), "=&r"(junk));
 }
 
 // A: accumulator whose column starts AT the limb being cleared (entries A[B..B+7] all data, carry -> A[B+8]).
@@ -182,9 +182,9 @@ __device__ __forceinline__ void redc_row(u32* A, u32* C, u32 hi) {
         "madc.lo.cc.u32 %6,  %17, " BNP_STR(BNP_P6) ", %6;  madc.hi.cc.u32 %7, %17, " BNP_STR(BNP_P6) ", %7;\n\t"
         "addc.u32 %8, 0, 0;"
         : "+r"(A[B]), "+r"(A[B + 1]), "+r"(A[B + 2]), "+r"(A[B + 3]), "+r"(A[B + 4]), "+r"(A[B + 5]),
-          "+r"(A[B + 6]), "+r"(A[B + 7]), "=r"(A[B + 8]), "+r"(C[D]), "+r"(C[D + 1]), "+r"(C[D + 2]),
-          "+r"(C[D + 3]), "+r"(C[D + 4]), "+r"(C[D + 5]), "+r"(C[D + 6]), "=r"(C[D + 7]), "=&r"(m), "=&r"(s),
-          "=r"(junk)
+          "+r"(A[B + 6]), "+r"(A[B + 7]), "=&r"(A[B + 8]), "+r"(C[D]), "+r"(C[D + 1]), "+r"(C[D + 2]),
+          "+r"(C[D + 3]), "+r"(C[D + 4]), "+r"(C[D + 5]), "+r"(C[D + 6]), "=&r"(C[D + 7]), "=&r"(m), "=&r"(s),
+          "=&r"(junk)
         : "r"(hi));
 }
 
@@ -200,8 +200,8 @@ __device__ __forceinline__ void fp_cond_sub_p(u32* r) {
         "subc.cc.u32 %6, %15, " BNP_STR(BNP_P6) ";\n\t"
         "subc.cc.u32 %7, %16, " BNP_STR(BNP_P7) ";\n\t"
         "subc.u32    %8, 0, 0;"
-        : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]),
-          "=r"(borrow)
+        : "=&r"(t[0]), "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]), "=&r"(t[7]),
+          "=&r"(borrow)
         : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]));
 #pragma unroll
     for (int i = 0; i < 8; i++) r[i] = borrow ? r[i] : t[i];
@@ -231,7 +231,7 @@ __device__ __forceinline__ void fp_redc(u32* r /*8*/, const u32* T /*16*/) {
         "addc.cc.u32 %5, %13, %21;\n\t"
         "addc.cc.u32 %6, %14, %22;\n\t"
         "addc.u32    %7, %15, %23;"
-        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+        : "=&r"(u[0]), "=&r"(u[1]), "=&r"(u[2]), "=&r"(u[3]), "=&r"(u[4]), "=&r"(u[5]), "=&r"(u[6]), "=&r"(u[7])
         : "r"(E[8]), "r"(E[9]), "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]),
           "r"(O[7]), "r"(O[8]), "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
     asm("add.cc.u32  %0, %8,  %16;\n\t"
@@ -242,7 +242,7 @@ __device__ __forceinline__ void fp_redc(u32* r /*8*/, const u32* T /*16*/) {
         "addc.cc.u32 %5, %13, %21;\n\t"
         "addc.cc.u32 %6, %14, %22;\n\t"
         "addc.u32    %7, %15, %23;"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7])
         : "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(T[8]),
           "r"(T[9]), "r"(T[10]), "r"(T[11]), "r"(T[12]), "r"(T[13]), "r"(T[14]), "r"(T[15]));
     fp_cond_sub_p(r);
@@ -262,7 +262,7 @@ __device__ __forceinline__ u32 add8(u32* r, const u32* a, const u32* b) {  // re
         "addc.cc.u32 %6, %15, %23;\n\t"
         "addc.cc.u32 %7, %16, %24;\n\t"
         "addc.u32    %8, 0, 0;"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(c)
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]),
           "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
     return c;
@@ -279,7 +279,7 @@ __device__ __forceinline__ u32 sub8(u32* r, const u32* a, const u32* b) {  // re
         "subc.cc.u32 %6, %15, %23;\n\t"
         "subc.cc.u32 %7, %16, %24;\n\t"
         "subc.u32    %8, 0, 0;"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(c)
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(b[0]),
           "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
     return c;
@@ -320,9 +320,9 @@ __device__ __forceinline__ u32 sub16(u32* r, const u32* a, const u32* b) {
         "subc.cc.u32 %14, %31, %47;\n\t"
         "subc.cc.u32 %15, %32, %48;\n\t"
         "subc.u32    %16, 0, 0;"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(c)
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]),
+          "=&r"(r[8]), "=&r"(r[9]), "=&r"(r[10]), "=&r"(r[11]), "=&r"(r[12]), "=&r"(r[13]), "=&r"(r[14]), "=&r"(r[15]),
+          "=&r"(c)
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8]),
           "r"(a[9]), "r"(a[10]), "r"(a[11]), "r"(a[12]), "r"(a[13]), "r"(a[14]), "r"(a[15]), "r"(b[0]), "r"(b[1]),
           "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(b[8]), "r"(b[9]), "r"(b[10]),

@@ -46,7 +46,7 @@ __device__ __forceinline__ void fp_sub_lazy(u32* r, const u32* a, const u32* b) 
         "addc.cc.u32 %5, %13, " BNP_STR(BNP_P5) ";\n\t"
         "addc.cc.u32 %6, %14, " BNP_STR(BNP_P6) ";\n\t"
         "addc.u32    %7, %15, " BNP_STR(BNP_P7) ";"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7])
         : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]));
 }
 
@@ -115,7 +115,7 @@ __device__ __forceinline__ void fp_reduce_small(u32* r, const u32* v /*9*/) {
         "addc.cc.u32 %4, %11, %18;\n\t"
         "addc.cc.u32 %5, %12, %19;\n\t"
         "addc.u32    %6, %13, %20;"
-        : "=r"(qp[1]), "=r"(qp[2]), "=r"(qp[3]), "=r"(qp[4]), "=r"(qp[5]), "=r"(qp[6]), "=r"(qp[7])
+        : "=&r"(qp[1]), "=&r"(qp[2]), "=&r"(qp[3]), "=&r"(qp[4]), "=&r"(qp[5]), "=&r"(qp[6]), "=&r"(qp[7])
         : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(O[0]), "r"(O[1]),
           "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]));
     // v - q*p < 2p < 2^255, so limb 8 of the difference is zero and limbs 0..7 suffice
@@ -140,7 +140,7 @@ __device__ __forceinline__ void mul9_add(u32* v /*9*/, const u32* a, const u32* 
         "addc.cc.u32 %5, %13, %21;\n\t"
         "addc.cc.u32 %6, %14, %22;\n\t"
         "addc.u32    %7, %15, %23;"
-        : "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8])
+        : "=&r"(v[1]), "=&r"(v[2]), "=&r"(v[3]), "=&r"(v[4]), "=&r"(v[5]), "=&r"(v[6]), "=&r"(v[7]), "=&r"(v[8])
         : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(O[0]),
           "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]));
 }
@@ -248,7 +248,7 @@ __device__ __forceinline__ void mul_small9(u32* t, u32 m, const u32* x) {
         "addc.cc.u32 %5, %13, %20;\n\t"
         "addc.cc.u32 %6, %14, %21;\n\t"
         "addc.u32    %7, %22, 0;"
-        : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8])
+        : "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]), "=&r"(t[7]), "=&r"(t[8])
         : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(O[0]), "r"(O[1]),
           "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]));
 }
