@@ -240,6 +240,38 @@ __global__ void __launch_bounds__(T) bnp_vm_kernel(VmArgs args) {
                     fp2_inv(r, x);
                     S.store(d, r);
                     break;
+                case BNP_OP_ADD:
+                    S.load(x, a);
+                    S.load(y, b);
+                    fp2_add(r, x, y);
+                    S.store(d, r);
+                    break;
+                case BNP_OP_SUB:
+                    S.load(x, a);
+                    S.load(y, b);
+                    fp2_sub(r, x, y);
+                    S.store(d, r);
+                    break;
+                case BNP_OP_DBL:
+                    S.load(x, a);
+                    fp2_add(r, x, x);
+                    S.store(d, r);
+                    break;
+                case BNP_OP_NEG:
+                    S.load(x, a);
+                    fp2_neg(r, x);
+                    S.store(d, r);
+                    break;
+                case BNP_OP_CONJ:
+                    S.load(x, a);
+                    fp2_conj(r, x);
+                    S.store(d, r);
+                    break;
+                case BNP_OP_MULXI:
+                    S.load(x, a);
+                    fp2_mul_xi(r, x);
+                    S.store(d, r);
+                    break;
                 default:
                     break;
             }

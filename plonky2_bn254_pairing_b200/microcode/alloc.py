@@ -133,8 +133,10 @@ def allocate(ops, n_slots):
             emit("SQR", d=d, a=src_slots[0], b=b, imm=o.flags)
         elif o.op == "MULFP":
             emit("MULFP", d=d, a=src_slots[0], b=src_slots[1], imm=o.imm)
-        elif o.op == "INV":
-            emit("INV", d=d, a=src_slots[0])
+        elif o.op in ("INV", "DBL", "NEG", "CONJ", "MULXI"):
+            emit(o.op, d=d, a=src_slots[0])
+        elif o.op in ("ADD", "SUB"):
+            emit(o.op, d=d, a=src_slots[0], b=src_slots[1])
         elif o.op == "STG":
             emit("STG", d=o.f_lo, a=src_slots[0], b=o.f_hi, imm=o.imm)
         elif o.op == "LIN":

@@ -73,7 +73,7 @@ def _terms_of(expr):
     return terms, K, ktot
 
 
-def fuse(ops, enable=True):
+def fuse(ops, enable=True, lin_trees=False):
     uses = {}
     user = {}
     defop = {}
@@ -90,7 +90,7 @@ def fuse(ops, enable=True):
             return False
         u = user[v]
         if u.op in LINEAR:
-            return True
+            return lin_trees
         return u.op in ("MUL", "SQR") and o.op in ("ADD", "SUB") and u.srcs.count(v) == 1
 
     out = []
@@ -146,6 +146,15 @@ def fuse(ops, enable=True):
         """Materialise linear value v (removing it from pending)."""
         v = res(v)
         o = pending[v]
+        if not lin_trees:
+            # elementary form: one dedicated opcode per modular step
+            pending.pop(v)
+            if o.op == "MOV":
+                alias[v] = need(o.srcs[0])
+                return
+            out.append(FOp(o.op, v, [need(s) for s in o.srcs]))
+            done.add(v)
+            return
         expr = expand(v, None)
         enc = _terms_of(expr) if expr else None
         if expr and enc is None:

@@ -103,6 +103,18 @@ def run(words, consts, arrays, n_slots, n_scratch):
             scratch[imm] = slots[a]
         elif op == "FILL":
             slots[d] = scratch[imm]
+        elif op == "ADD":
+            slots[d] = ((slots[a][0] + slots[b][0]) % P, (slots[a][1] + slots[b][1]) % P)
+        elif op == "SUB":
+            slots[d] = ((slots[a][0] - slots[b][0]) % P, (slots[a][1] - slots[b][1]) % P)
+        elif op == "DBL":
+            slots[d] = (2 * slots[a][0] % P, 2 * slots[a][1] % P)
+        elif op == "NEG":
+            slots[d] = (-slots[a][0] % P, -slots[a][1] % P)
+        elif op == "CONJ":
+            slots[d] = (slots[a][0], -slots[a][1] % P)
+        elif op == "MULXI":
+            slots[d] = ((9 * slots[a][0] - slots[a][1]) % P, (slots[a][0] + 9 * slots[a][1]) % P)
         elif op == "INV":
             x = slots[a]
             n = (x[0] * x[0] + x[1] * x[1]) % P
@@ -132,7 +144,8 @@ def walk(words):
             yield op, 0
             break
         else:
-            yield op, {"LDC": 1, "LDG": 1, "STG": 1, "SPILL": 1, "FILL": 1, "INV": 2}[op]
+            yield op, {"LDC": 1, "LDG": 1, "STG": 1, "SPILL": 1, "FILL": 1, "INV": 2, "ADD": 3, "SUB": 3, "DBL": 2,
+                       "NEG": 2, "CONJ": 2, "MULXI": 2}[op]
 
 
 def work(words):

@@ -15,7 +15,9 @@ flow is uniform across the grid.  One instruction word is 64 bits, eight byte-wi
 MUL / SQR take optional pre-additions (Karatsuba operands are sums of two slots):
     MUL  d = (a [+-b]) * (c [+-e])     imm bit0: b present, bit1: b subtracted, bit2: e present, bit3: e subtracted
     SQR  d = (a [+-b])^2               imm bit0: b present, bit1: b subtracted
-LIN is the only linear opcode: a variable-length instruction
+ADD / SUB / DBL / NEG / CONJ / MULXI are the elementary linear opcodes (one modular step each).
+LIN is an optional fused form (kept for experiments; measured slower on B200 than the elementary ops,
+see DESIGN.md section 6): a variable-length instruction
     d = sum_i diag(m0_i, m1_i) * x_i  +  xi * sum_j diag(m0_j, m1_j) * x_j        (xi = 9 + u)
 with small signed integer multipliers per Fq component (this subsumes add, sub, neg, double, conj,
 multiplication by xi and by small constants).  Header word: d, a = number of terms, imm = K (the
@@ -37,6 +39,12 @@ OPS = [
     "SPILL",  # scratch[imm] = a
     "FILL",   # d = scratch[imm]
     "INV",    # d = 1 / a   (Fq2)
+    "ADD",    # d = a + b            elementary linear ops: canonical in, canonical out
+    "SUB",    # d = a - b
+    "DBL",    # d = 2 a
+    "NEG",    # d = -a
+    "CONJ",   # d = conj(a)
+    "MULXI",  # d = (9 + u) a
 ]
 OPCODE = {name: i for i, name in enumerate(OPS)}
 

@@ -22,8 +22,10 @@ def run(name, arrays, n_slots):
             assert max(d, a, bb, c, e) < n_slots
         elif op in ("SQR", "MULFP"):
             assert max(d, a, bb) < n_slots
-        elif op == "INV":
+        elif op in ("INV", "DBL", "NEG", "CONJ", "MULXI"):
             assert max(d, a) < n_slots
+        elif op in ("ADD", "SUB"):
+            assert max(d, a, bb) < n_slots
         elif op == "SPILL":
             assert a < n_slots and imm < max(al.n_scratch, 1)
         elif op == "FILL":
@@ -132,8 +134,10 @@ def test_encode_decode_roundtrip_and_naf():
     assert programs.SIX_U_PLUS_2_NAF == O.SIX_U_PLUS_2_NAF
 
 
-def test_optest_program_matches_expectations():
-    """The op-level GPU test's expected values, checked here against the interpreter (incl. edge values)."""
+@pytest.mark.parametrize("lin_trees", [False, True])
+def test_optest_program_matches_expectations(lin_trees):
+    """The op-level GPU test's expected values, checked here against the interpreter (incl. edge values),
+    for both lowerings of the linear operations (elementary opcodes / fused LIN trees)."""
     import optest_expect as X
 
     rows = X.edge_rows(random.Random(7), n_random=24)
@@ -141,7 +145,7 @@ def test_optest_program_matches_expectations():
         pool = ConstPool()
         b = programs.build_program("optest", pool)
         from plonky2_bn254_pairing_b200.microcode import fuse
-        al = alloc.allocate(fuse.fuse(b.ops), 14)
+        al = alloc.allocate(fuse.fuse(b.ops, lin_trees=lin_trees), 14)
         arrays = {isa.ARR_F12: r, isa.ARR_OUT: {}}
         interp.run(al.words, pool.values, arrays, al.n_slots, al.n_scratch)
         want = X.expected(r)
@@ -157,7 +161,7 @@ def test_fusion_preserves_results_and_cuts_slot_moves():
     b = programs.build_program("pairing_v0", pool)
     res = {}
     for en in (False, True):
-        al = alloc.allocate(fuse.fuse(b.ops, enable=en), 14)
+        al = alloc.allocate(fuse.fuse(b.ops, enable=en, lin_trees=en), 14)
         arrays = g1g2([PTS[3]])
         arrays[isa.ARR_OUT] = {}
         interp.run(al.words, pool.values, arrays, al.n_slots, al.n_scratch)
