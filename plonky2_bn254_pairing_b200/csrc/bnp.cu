@@ -137,7 +137,6 @@ int init_device(int dev) {
     CK(cudaMalloc(&c.counters, BNP_NCOUNTERS * sizeof(u32)));
     if (BNP_NCONST > BNP_MAX_CONST) return BNP_EUNSUPPORTED;
     CK(cudaMemcpyToSymbol(BNP_CONSTS, BNP_CONST_TABLE, (size_t)BNP_NCONST * 64));
-    CK(cudaMemcpyToSymbol(BNP_KP, BNP_KP_TABLE, sizeof(u32) * 9 * (BNP_LIN_MAX_K + 1)));
     c.d_prog.resize(BNP_NPROG, nullptr);
     for (uint32_t i = 0; i < BNP_NPROG; i++) {
         const size_t bytes = (size_t)BNP_PROGRAMS[i].len * 8;

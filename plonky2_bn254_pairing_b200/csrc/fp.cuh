@@ -84,6 +84,19 @@ __device__ __forceinline__ void chain_full(u32* x, u32 s, u32 q0, u32 q1, u32 q2
         : "r"(s), "r"(q0), "r"(q1), "r"(q2), "r"(q3));
 }
 
+// accumulating form for the LIN engine: x[B .. B+7] += s * (q0..q3), carry ADDED to x[B+8]
+template <int B>
+__device__ __forceinline__ void chain_acc(u32* x, u32 s, u32 q0, u32 q1, u32 q2, u32 q3) {
+    asm("mad.lo.cc.u32  %0, %9, %10, %0; madc.hi.cc.u32 %1, %9, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %11, %2; madc.hi.cc.u32 %3, %9, %11, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %12, %4; madc.hi.cc.u32 %5, %9, %12, %5;\n\t"
+        "madc.lo.cc.u32 %6, %9, %13, %6; madc.hi.cc.u32 %7, %9, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(x[B]), "+r"(x[B + 1]), "+r"(x[B + 2]), "+r"(x[B + 3]), "+r"(x[B + 4]), "+r"(x[B + 5]),
+          "+r"(x[B + 6]), "+r"(x[B + 7]), "+r"(x[B + 8])
+        : "r"(s), "r"(q0), "r"(q1), "r"(q2), "r"(q3));
+}
+
 // ---------------------------------------------------------------------------------------------
 // 256 x 256 -> 512-bit product, 64 IMAD.WIDE + 7 carry captures + 15 merge adds
 // ---------------------------------------------------------------------------------------------
@@ -207,9 +220,43 @@ __device__ __forceinline__ void fp_cond_sub_p(u32* r) {
     for (int i = 0; i < 8; i++) r[i] = borrow ? r[i] : t[i];
 }
 
+// r = (r >= c) ? r - c : r for a constant c given as eight limbs (c = 2p, 4p: the canonicalisation ladder
+// of lazily bounded results)
+__device__ __forceinline__ void fp_cond_sub_const(u32* r, u32 c0, u32 c1, u32 c2, u32 c3, u32 c4, u32 c5, u32 c6, u32 c7) {
+    u32 t[8], borrow;
+    asm("sub.cc.u32  %0, %9,  %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32    %8, 0, 0;"
+        : "=&r"(t[0]), "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]), "=&r"(t[7]),
+          "=&r"(borrow)
+        : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(c0), "r"(c1), "r"(c2),
+          "r"(c3), "r"(c4), "r"(c5), "r"(c6), "r"(c7));
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = borrow ? r[i] : t[i];
+}
+
+// r in [0, 2p * (lvl + 1)) -> canonical residue; lvl is warp-uniform (an instruction field)
+__device__ __forceinline__ void fp_canon(u32* r, u32 lvl) {
+    if (lvl >= 2u)
+        fp_cond_sub_const(r, 0x61f3f51cu, 0xf082305bu, 0xa1c72a34u, 0x5e05aa45u, 0x06056176u, 0xe14116dau, 0x84c680a6u,
+                          0xc19139cbu);  // 4p
+    if (lvl >= 1u)
+        fp_cond_sub_const(r, 0xb0f9fa8eu, 0x7841182du, 0xd0e3951au, 0x2f02d522u, 0x0302b0bbu, 0x70a08b6du, 0xc2634053u,
+                          0x60c89ce5u);  // 2p
+    fp_cond_sub_const(r, (u32)BNP_P0, (u32)BNP_P1, (u32)BNP_P2, (u32)BNP_P3, (u32)BNP_P4, (u32)BNP_P5, (u32)BNP_P6,
+                      (u32)BNP_P7);
+}
+
 // Montgomery reduction of a 512-bit T < p * 2^256: r = T / 2^256 mod p, canonical.
 // 8 IMAD + 64 IMAD.WIDE.
-__device__ __forceinline__ void fp_redc(u32* r /*8*/, const u32* T /*16*/) {
+// fp_redc_lazy: any T < 2^512 - p * 2^256; the result is T / 2^256 + (< p), NOT canonicalised.
+__device__ __forceinline__ void fp_redc_lazy(u32* r /*8*/, const u32* T /*16*/) {
     u32 E[17], O[16];
 #pragma unroll
     for (int i = 0; i < 8; i++) E[i] = T[i];
@@ -245,6 +292,10 @@ __device__ __forceinline__ void fp_redc(u32* r /*8*/, const u32* T /*16*/) {
         : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7])
         : "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(T[8]),
           "r"(T[9]), "r"(T[10]), "r"(T[11]), "r"(T[12]), "r"(T[13]), "r"(T[14]), "r"(T[15]));
+}
+
+__device__ __forceinline__ void fp_redc(u32* r /*8*/, const u32* T /*16*/) {
+    fp_redc_lazy(r, T);
     fp_cond_sub_p(r);
 }
 

@@ -28,6 +28,60 @@ __device__ __forceinline__ void fp2_mul(Fp2& r, const Fp2& a, const Fp2& b, bool
     if (lazy) fp_cond_sub_p(r.c1);
 }
 
+// Wide (unreduced) forms used by the sequencer's product-class epilogue: T0, T1 are the 512-bit values whose
+// Montgomery reductions are the two components of the result.
+//   mul:   T0 = a0 b0 - a1 b1 (+ p 2^256 when negative) in [0, p 2^256),  T1 = a0 b1 + a1 b0
+//   sqr:   T0 = (a0 + a1)(a0 - a1),  T1 = 2 a0 a1         (a canonical)
+//   mulfp: T0 = a0 s, T1 = a1 s
+__device__ __forceinline__ void fp2_mul_wide(u32* T0, u32* T1, const Fp2& a, const Fp2& b) {
+    u32 sa[8], sb[8];
+    add8(sa, a.c0, a.c1);
+    add8(sb, b.c0, b.c1);
+    u32 P1[16];
+    fp_mul_wide(T0, a.c0, b.c0);
+    fp_mul_wide(P1, a.c1, b.c1);
+    fp_mul_wide(T1, sa, sb);
+    sub16(T1, T1, T0);
+    sub16(T1, T1, P1);
+    u32 borrow = sub16(T0, T0, P1);
+    add_p_masked(T0 + 8, borrow);
+}
+
+__device__ __forceinline__ void fp2_sqr_wide(u32* T0, u32* T1, const Fp2& a) {
+    u32 s[8], d[8], t[8];
+    add8(s, a.c0, a.c1);
+    fp_sub(d, a.c0, a.c1);
+    add8(t, a.c0, a.c0);
+    fp_mul_wide(T0, s, d);
+    fp_mul_wide(T1, t, a.c1);
+}
+
+__device__ __forceinline__ void fp2_mul_fp_wide(u32* T0, u32* T1, const Fp2& a, const u32* s) {
+    fp_mul_wide(T0, a.c0, s);
+    fp_mul_wide(T1, a.c1, s);
+}
+
+// T[8..15] += h (no carry out: the sequencer's bound analysis guarantees T + h 2^256 < 2^512)
+__device__ __forceinline__ void wide_add_hi(u32* T, const u32* h) {
+    asm("add.cc.u32  %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\t"
+        "addc.cc.u32 %3, %3, %11;\n\t"
+        "addc.cc.u32 %4, %4, %12;\n\t"
+        "addc.cc.u32 %5, %5, %13;\n\t"
+        "addc.cc.u32 %6, %6, %14;\n\t"
+        "addc.u32    %7, %7, %15;"
+        : "+r"(T[8]), "+r"(T[9]), "+r"(T[10]), "+r"(T[11]), "+r"(T[12]), "+r"(T[13]), "+r"(T[14]), "+r"(T[15])
+        : "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]));
+}
+
+// r = p - a for canonical a (a = 0 gives p, which is fine for a lazy term)
+__device__ __forceinline__ void fp_p_minus(u32* r, const u32* a) {
+    const u32 pp[8] = {(u32)BNP_P0, (u32)BNP_P1, (u32)BNP_P2, (u32)BNP_P3,
+                       (u32)BNP_P4, (u32)BNP_P5, (u32)BNP_P6, (u32)BNP_P7};
+    sub8(r, pp, a);
+}
+
 // lazy pre-additions for MUL / SQR operands: results in [0, 2p), no reduction
 __device__ __forceinline__ void fp2_add_lazy(Fp2& r, const Fp2& a, const Fp2& b) {
     add8(r.c0, a.c0, b.c0);
@@ -211,28 +265,8 @@ __device__ __forceinline__ void fp2_inv(Fp2& r, const Fp2& a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// LIN: lazily accumulated linear combinations.  Accumulators are 9-limb two's-complement integers.
+// LIN support: reduction of a lazily accumulated nine-limb value
 // ---------------------------------------------------------------------------------------------
-
-// a (9 limbs, signed) += neg ? -t : t, t = 9-limb non-negative value
-__device__ __forceinline__ void acc9_addsub(u32* a, const u32* t, u32 neg) {
-    const u32 mask = 0u - neg;
-    u32 junk;
-    asm("add.cc.u32  %9, %19, 0xffffffff;\n\t"   // carry = neg
-        "addc.cc.u32 %0, %0, %10;\n\t"
-        "addc.cc.u32 %1, %1, %11;\n\t"
-        "addc.cc.u32 %2, %2, %12;\n\t"
-        "addc.cc.u32 %3, %3, %13;\n\t"
-        "addc.cc.u32 %4, %4, %14;\n\t"
-        "addc.cc.u32 %5, %5, %15;\n\t"
-        "addc.cc.u32 %6, %6, %16;\n\t"
-        "addc.cc.u32 %7, %7, %17;\n\t"
-        "addc.u32    %8, %8, %18;"
-        : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]),
-          "=&r"(junk)
-        : "r"(t[0] ^ mask), "r"(t[1] ^ mask), "r"(t[2] ^ mask), "r"(t[3] ^ mask), "r"(t[4] ^ mask), "r"(t[5] ^ mask),
-          "r"(t[6] ^ mask), "r"(t[7] ^ mask), "r"(t[8] ^ mask), "r"(neg));
-}
 
 // t (9 limbs) = m * x, m < 2^10, x 8 limbs
 __device__ __forceinline__ void mul_small9(u32* t, u32 m, const u32* x) {
@@ -251,32 +285,6 @@ __device__ __forceinline__ void mul_small9(u32* t, u32 m, const u32* x) {
         : "=&r"(t[1]), "=&r"(t[2]), "=&r"(t[3]), "=&r"(t[4]), "=&r"(t[5]), "=&r"(t[6]), "=&r"(t[7]), "=&r"(t[8])
         : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(O[0]), "r"(O[1]),
           "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]));
-}
-
-// one Fq component of one term: acc += m * x (m signed, |m| <= 31)
-__device__ __forceinline__ void acc9_term(u32* acc, int m, const u32* x) {
-    const u32 neg = m < 0 ? 1u : 0u;
-    const u32 am = (u32)(m < 0 ? -m : m);
-    u32 t[9];
-    if (am == 1u) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) t[i] = x[i];
-        t[8] = 0u;
-    } else {
-        mul_small9(t, am, x);
-    }
-    acc9_addsub(acc, t, neg);
-}
-
-// t = 9 * a for a signed 9-limb a (two's complement shift-and-add; |a| < 2^270 so nothing overflows)
-__device__ __forceinline__ void acc9_times9(u32* t, const u32* a) {
-    u32 s[9];
-    s[0] = a[0] << 3;
-#pragma unroll
-    for (int i = 1; i < 9; i++) s[i] = __funnelshift_l(a[i - 1], a[i], 3);
-#pragma unroll
-    for (int i = 0; i < 9; i++) t[i] = a[i];
-    acc9_addsub(t, s, 0u);
 }
 
 // v (9 limbs, 0 <= v < 1024 p) -> canonical residue.  Quotient estimate from the top 32 bits:

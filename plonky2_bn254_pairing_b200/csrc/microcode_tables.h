@@ -15,6 +15,5 @@ struct BnpProgram {
 
 extern const uint32_t BNP_NCONST;
 extern const uint32_t BNP_CONST_TABLE[][16];
-extern const uint32_t BNP_KP_TABLE[][9];
 extern const uint32_t BNP_NPROG;
 extern const BnpProgram BNP_PROGRAMS[];

@@ -71,57 +71,176 @@ __device__ __forceinline__ void stg_fp(u64* arr, u32 f, u32 n, u32 e, const u32*
     for (int j = 0; j < 4; j++) p[(size_t)j * n] = (u64)r[2 * j] | ((u64)r[2 * j + 1] << 32);
 }
 
-// K * p for K = 0 .. BNP_LIN_MAX_K (9 limbs each): the offset that makes a LIN accumulator non-negative
-__device__ __constant__ u32 BNP_KP[BNP_LIN_MAX_K + 1][9];
+// ---------------------------------------------------------------------------------------------
+// LIN engine.  Each output component is a lazily accumulated sum of small multiples of Fq halves of
+// slots:  out_c = sum_j mult_j * (neg_j ? p - z_j : z_j)  <  1024 p,  reduced once by a quotient estimate.
+// An entry is one pair of 4-deep IMAD.WIDE chains into 64-bit-column accumulators (E: even limb
+// positions, O: odd) - the accumulation itself costs no ALU instructions.
+// Entries are 16 bits, [slot:8][half:1][neg:1][mult:6], and come in PAIRS (component 0, component 1) so
+// that every step runs two independent accumulations; the loop is software-pipelined by hand (the
+// operands of pair j+1 are fetched while pair j is accumulated) because a warp has only one
+// other warp on its scheduler to hide the shared-memory latency.
+// Two pairs per 64-bit word; the first six pairs arrive in registers, later ones are read from `more`.
+// ---------------------------------------------------------------------------------------------
+#define BNP_LIN_FETCH(J, ZA, ZB, TA, TB)                                      \
+    {                                                                         \
+        u64 w_ = w1;                                                          \
+        if ((J) >= 2u) w_ = w2;                                               \
+        if ((J) >= 4u) w_ = w3;                                               \
+        if ((J) >= 6u) w_ = __ldg(more + ((J) >> 1));                         \
+        const u32 t_ = (u32)(w_ >> (32u * ((J)&1u)));                         \
+        TA = t_ & 0xffffu;                                                    \
+        TB = t_ >> 16;                                                        \
+        S.load_half(ZA, TA & 0xffu, (TA >> 8) & 1u);                          \
+        S.load_half(ZB, TB & 0xffu, (TB >> 8) & 1u);                          \
+    }
+#define BNP_LIN_ACC(ZA, ZB, TA, TB)                                           \
+    {                                                                         \
+        if (TA & 0x200u) fp_p_minus(ZA, ZA);                                  \
+        if (TB & 0x200u) fp_p_minus(ZB, ZB);                                  \
+        chain_acc<0>(E0, TA >> 10, ZA[0], ZA[2], ZA[4], ZA[6]);               \
+        chain_acc<0>(E1, TB >> 10, ZB[0], ZB[2], ZB[4], ZB[6]);               \
+        chain_acc<0>(O0, TA >> 10, ZA[1], ZA[3], ZA[5], ZA[7]);               \
+        chain_acc<0>(O1, TB >> 10, ZB[1], ZB[3], ZB[5], ZB[7]);               \
+    }
 
-// LIN: d = sum_i diag(m0,m1) x_i + xi * sum_j diag(m0,m1) x_j, accumulated lazily, reduced once.
-// `pc` points at the first term word; returns the advanced pointer.
+// v = E + (O << 32): nine limbs (the total is below 2^264, so limb 9 of either part is zero)
+__device__ __forceinline__ void lin_merge(u32* v, const u32* E, const u32* O) {
+    v[0] = E[0];
+    asm("add.cc.u32  %0, %8,  %16;\n\t"
+        "addc.cc.u32 %1, %9,  %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32    %7, %15, %23;"
+        : "=&r"(v[1]), "=&r"(v[2]), "=&r"(v[3]), "=&r"(v[4]), "=&r"(v[5]), "=&r"(v[6]), "=&r"(v[7]), "=&r"(v[8])
+        : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(O[0]),
+          "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]));
+}
+
 template <int T>
-__device__ __forceinline__ const u64* vm_lin(const Slots<T>& S, const u64* pc, u32 d, u32 nterms, u32 K) {
-    u32 A0[9], A1[9], X0[9], X1[9];
+__device__ __forceinline__ void vm_lin(const Slots<T>& S, Fp2& out, u32 n, u64 w1, u64 w2, u64 w3, const u64* more) {
+    u32 E0[10], O0[10], E1[10], O1[10];
 #pragma unroll
-    for (int i = 0; i < 9; i++) A0[i] = A1[i] = X0[i] = X1[i] = 0u;
-    bool any_xi = false;
-    u64 w = 0;
+    for (int i = 0; i < 10; i++) E0[i] = O0[i] = E1[i] = O1[i] = 0u;
+    u32 za[8], zb[8], ya[8], yb[8], ta, tb, ua, ub;
+    BNP_LIN_FETCH(0u, za, zb, ta, tb);
 #pragma unroll 1
-    for (u32 j = 0; j < nterms; j++) {
-        if ((j & 1u) == 0u) w = __ldg(pc++);
-        const u32 t = (j & 1u) ? (u32)(w >> 32) : (u32)w;
-        const u32 slot = t & 0xffu;
-        const bool xi = (t >> 8) & BNP_LIN_XI;
-        const int m0 = (int)(signed char)((t >> 16) & 0xffu);
-        const int m1 = (int)(signed char)(t >> 24);
+    for (u32 j = 0;; j += 2u) {
+        if (j + 1u < n) BNP_LIN_FETCH(j + 1u, ya, yb, ua, ub);
+        BNP_LIN_ACC(za, zb, ta, tb);
+        if (j + 1u >= n) break;
+        if (j + 2u < n) BNP_LIN_FETCH(j + 2u, za, zb, ta, tb);
+        BNP_LIN_ACC(ya, yb, ua, ub);
+        if (j + 2u >= n) break;
+    }
+    u32 v0[9], v1[9];
+    lin_merge(v0, E0, O0);
+    lin_merge(v1, E1, O1);
+    fp_reduce_lazy(out.c0, v0);
+    fp_reduce_lazy(out.c1, v1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Product class (MUL / SQR / MULFP), one fully inlined copy per opcode so that ptxas can overlap the
+// operand loads, the products and the reductions:
+//   T = wide product;  T += 2^256 * hi terms;  r' = canon(redc(T));  [S[d] = r'];  [S[d2] = LIN(r', ...)]
+// On entry `pc` points at the word after the instruction; on exit `ins` holds the next instruction
+// and `pc` points past it.  Five words are fetched up front (extension word, entry words, next instruction).
+// ---------------------------------------------------------------------------------------------
+template <int T, int OP>
+__device__ __forceinline__ void vm_product(const Slots<T>& S, const u64*& pc, u64& ins, u32 d, u32 a, u32 b, u32 c,
+                                           u32 ee, u32 imm) {
+    const u64* p0 = pc;
+    const u64 w0 = __ldg(p0), w1 = __ldg(p0 + 1), w2 = __ldg(p0 + 2), w3 = __ldg(p0 + 3), w4 = __ldg(p0 + 4);
+    u32 T0[16], T1[16];
+    if (OP == BNP_OP_MUL) {
+        Fp2 x, y;
+        S.load(x, a);
+        S.load(y, c);
+        if (imm & (BNP_MUL_B | BNP_MUL_E)) {  // Karatsuba operands: (a +- b) * (c +- e), sums kept lazy (< 2p)
+            Fp2 t;
+            if (imm & BNP_MUL_B) {
+                S.load(t, b);
+                if (imm & BNP_MUL_BNEG) fp2_sub_lazy(x, x, t); else fp2_add_lazy(x, x, t);
+                if (imm & BNP_MUL_BCANON) {
+                    fp_cond_sub_p(x.c0);
+                    fp_cond_sub_p(x.c1);
+                }
+            }
+            if (imm & BNP_MUL_E) {
+                S.load(t, ee);
+                if (imm & BNP_MUL_ENEG) fp2_sub_lazy(y, y, t); else fp2_add_lazy(y, y, t);
+            }
+        }
+        fp2_mul_wide(T0, T1, x, y);
+    } else if (OP == BNP_OP_SQR) {
         Fp2 x;
-        S.load(x, slot);
-        if (xi) {
-            any_xi = true;
-            if (m0) acc9_term(X0, m0, x.c0);
-            if (m1) acc9_term(X1, m1, x.c1);
-        } else {
-            if (m0) acc9_term(A0, m0, x.c0);
-            if (m1) acc9_term(A1, m1, x.c1);
+        S.load(x, a);
+        if (imm & BNP_MUL_B) {
+            Fp2 y;
+            S.load(y, b);
+            if (imm & BNP_MUL_BNEG) fp2_sub(x, x, y); else fp2_add(x, x, y);
+        }
+        fp2_sqr_wide(T0, T1, x);
+    } else {
+        Fp2 x;
+        u32 s[8];
+        S.load(x, a);
+        S.load_half(s, b, (imm & BNP_MULFP_HALF) ? 1u : 0u);
+        fp2_mul_fp_wide(T0, T1, x, s);
+    }
+    u32 np = 0, d2 = 0;  // np: entry pairs of the post LIN
+    bool store_r = true;
+    if (imm & BNP_MUL_EXT) {
+        const u32 xl = (u32)w0, xh = (u32)(w0 >> 32);
+        d2 = xl & 0xffu;
+        const u32 hflags = xh & 0xffu;
+        np = (xh >> 8) & 0xffu;
+        store_r = np == 0u || (hflags & BNP_EXT_STORE_R);
+        const u32 n_hi = hflags & 3u;
+#pragma unroll 1
+        for (u32 i = 0; i < n_hi; i++) {
+            Fp2 h;
+            S.load(h, (xl >> (8u * (i + 1u))) & 0xffu);
+            if (hflags & (4u << i)) {
+                fp_p_minus(h.c0, h.c0);
+                fp_p_minus(h.c1, h.c1);
+            }
+            wide_add_hi(T0, h.c0);
+            wide_add_hi(T1, h.c1);
         }
     }
-    if (any_xi) {
-        // (A0, A1) += xi * (X0, X1) = (9 X0 - X1, X0 + 9 X1)
-        u32 n0[9], n1[9];
-        acc9_times9(n0, X0);
-        acc9_times9(n1, X1);
-        acc9_addsub(A0, n0, 0u);
-        acc9_addsub(A0, X1, 1u);
-        acc9_addsub(A1, X0, 0u);
-        acc9_addsub(A1, n1, 0u);
-    }
-    u32 kp[9];
-#pragma unroll
-    for (int i = 0; i < 9; i++) kp[i] = BNP_KP[K][i];
-    acc9_addsub(A0, kp, 0u);
-    acc9_addsub(A1, kp, 0u);
     Fp2 r;
-    fp_reduce_lazy(r.c0, A0);
-    fp_reduce_lazy(r.c1, A1);
-    S.store(d, r);
-    return pc;
+    fp_redc_lazy(r.c0, T0);
+    fp_redc_lazy(r.c1, T1);
+    fp_canon(r.c0, (imm >> BNP_MUL_CANON_SHIFT) & 3u);
+    fp_canon(r.c1, (imm >> (BNP_MUL_CANON_SHIFT + 2)) & 3u);
+    if (!(imm & BNP_MUL_EXT)) {
+        S.store(d, r);
+        ins = w0;
+        pc = p0 + 1;
+        return;
+    }
+    const u32 nw = (np + 1u) >> 1;  // entry words
+    if (np) {
+        S.store(store_r ? d : d2, r);    // park r' where the entries expect it
+        Fp2 o;
+        vm_lin<T>(S, o, np, w1, w2, w3, p0 + 1);
+        S.store(d2, o);
+    } else {
+        S.store(d, r);
+    }
+    // next instruction: inside the prefetched window unless the entry list was long
+    u64 nx = w1;
+    if (nw == 1u) nx = w2;
+    if (nw == 2u) nx = w3;
+    if (nw == 3u) nx = w4;
+    if (nw > 3u) nx = __ldg(p0 + 1 + nw);
+    ins = nx;
+    pc = p0 + 2 + nw;
 }
 
 template <int T>
@@ -154,49 +273,32 @@ __global__ void __launch_bounds__(T) bnp_vm_kernel(VmArgs args) {
             const u32 op = lo & 0xffu, d = (lo >> 8) & 0xffu, a = (lo >> 16) & 0xffu, b = lo >> 24;
             const u32 c = hi & 0xffu, ee = (hi >> 8) & 0xffu, imm = hi >> 16;
             if (op == BNP_OP_END) break;
-            if (op == BNP_OP_LIN) {
-                pc = vm_lin<T>(S, pc, d, a, imm);
-                ins = __ldg(pc++);
+            if (op == BNP_OP_MUL) {
+                vm_product<T, BNP_OP_MUL>(S, pc, ins, d, a, b, c, ee, imm);
+                continue;
+            }
+            if (op == BNP_OP_SQR) {
+                vm_product<T, BNP_OP_SQR>(S, pc, ins, d, a, b, c, ee, imm);
+                continue;
+            }
+            if (op == BNP_OP_MULFP) {
+                vm_product<T, BNP_OP_MULFP>(S, pc, ins, d, a, b, c, ee, imm);
+                continue;
+            }
+            if (op == BNP_OP_LIN) {  // d = LIN(slots), a = number of entry pairs
+                const u32 nw = (a + 1u) >> 1;
+                const u64 w1 = __ldg(pc), w2 = __ldg(pc + 1), w3 = __ldg(pc + 2);
+                const u64 nx = __ldg(pc + nw);
+                Fp2 o;
+                vm_lin<T>(S, o, a, w1, w2, w3, pc);
+                S.store(d, o);
+                ins = nx;
+                pc += nw + 1;
                 continue;
             }
             const u64 nxt = __ldg(pc++);  // prefetch (every program ends with END followed by padding)
             Fp2 x, y, r;
             switch (op) {
-                case BNP_OP_MUL: {
-                    S.load(x, a);
-                    S.load(y, c);
-                    if (imm) {  // Karatsuba operands: (a +- b) * (c +- e), sums kept lazy (< 2p)
-                        Fp2 t;
-                        if (imm & BNP_MUL_B) {
-                            S.load(t, b);
-                            if (imm & BNP_MUL_BNEG) fp2_sub_lazy(x, x, t); else fp2_add_lazy(x, x, t);
-                        }
-                        if (imm & BNP_MUL_E) {
-                            S.load(t, ee);
-                            if (imm & BNP_MUL_ENEG) fp2_sub_lazy(y, y, t); else fp2_add_lazy(y, y, t);
-                        }
-                    }
-                    fp2_mul(r, x, y, imm != 0);
-                    S.store(d, r);
-                    break;
-                }
-                case BNP_OP_SQR:
-                    S.load(x, a);
-                    if (imm & BNP_MUL_B) {
-                        S.load(y, b);
-                        if (imm & BNP_MUL_BNEG) fp2_sub(x, x, y); else fp2_add(x, x, y);
-                    }
-                    fp2_sqr(r, x);
-                    S.store(d, r);
-                    break;
-                case BNP_OP_MULFP: {
-                    u32 s[8];
-                    S.load(x, a);
-                    S.load_half(s, b, imm & 1u);
-                    fp2_mul_fp(r, x, s);
-                    S.store(d, r);
-                    break;
-                }
                 case BNP_OP_LDC:
 #pragma unroll
                     for (int i = 0; i < 8; i++) {

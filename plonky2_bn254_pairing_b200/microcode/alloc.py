@@ -22,10 +22,10 @@ def allocate(ops, n_slots):
     uses = defaultdict(list)
     defop = {}
     for i, o in enumerate(ops):
-        for s in o.srcs:
+        for s in o.all_srcs():
             uses[s].append(i)
-        if o.dst is not None:
-            defop[o.dst] = o
+        for v in ([o.dst] if o.dst is not None else []) + ([o.dst2] if o.dst2 is not None else []):
+            defop[v] = o
     upos = defaultdict(int)
 
     def next_use(v, i):
@@ -50,6 +50,9 @@ def allocate(ops, n_slots):
         words.append(isa.encode(op, **kw))
         stats[op] += 1
 
+    def remat(v):
+        return defop[v].op in REMAT
+
     def release(v):
         s = loc.pop(v, None)
         if s is not None:
@@ -69,13 +72,13 @@ def allocate(ops, n_slots):
             if v in protect:
                 continue
             nu = next_use(v, i)
-            cheap = defop[v].op in REMAT or v in scratch_of  # eviction needs no store
+            cheap = remat(v) or v in scratch_of  # eviction needs no store
             key = nu * 2 + (1 if cheap else 0)
             if key > best_key:
                 best, best_key = s, key
         assert best is not None, "not enough slots for one instruction"
         v = slot_val[best]
-        if next_use(v, i) != INF and defop[v].op not in REMAT and v not in scratch_of:
+        if next_use(v, i) != INF and not remat(v) and v not in scratch_of:
             if free_scratch:
                 sc = free_scratch.pop()
             else:
@@ -104,35 +107,69 @@ def allocate(ops, n_slots):
     for i, o in enumerate(ops):
         if o.op in REMAT:
             continue  # materialised at first use
-        protect = set(o.srcs)
-        assert len(protect) + 1 <= n_slots, "instruction needs more slots than available"
-        for v in o.srcs:
+        all_srcs = o.all_srcs()
+        protect = set(all_srcs)
+        dsts = o.dsts()
+        assert len(protect) + len(dsts) <= n_slots, "instruction needs more slots than available"
+        for v in all_srcs:
             materialise(v, i, protect)
-        src_slots = [loc[v] for v in o.srcs]
-        for v in set(o.srcs):
-            if next_use(v, i + 1) == INF:
-                release(v)  # last use: the destination may reuse the slot (handlers read before they write)
-        d = 0
-        if o.dst is not None:
-            d = take_slot(i + 1, protect=set(v for v in o.srcs if v in loc))
-            loc[o.dst] = d
-            slot_val[d] = o.dst
-        if o.op == "MUL":
-            k = 0
-            a = src_slots[k]; k += 1
-            b = 0
-            if o.flags & isa.MUL_B:
-                b = src_slots[k]; k += 1
-            c = src_slots[k]; k += 1
-            e = 0
-            if o.flags & isa.MUL_E:
-                e = src_slots[k]; k += 1
-            emit("MUL", d=d, a=a, b=b, c=c, e=e, imm=o.flags)
-        elif o.op == "SQR":
-            b = src_slots[1] if o.flags & isa.MUL_B else 0
-            emit("SQR", d=d, a=src_slots[0], b=b, imm=o.flags)
-        elif o.op == "MULFP":
-            emit("MULFP", d=d, a=src_slots[0], b=src_slots[1], imm=o.imm)
+        sl = {v: loc[v] for v in all_srcs}
+        # last use: a destination may reuse the slot (handlers read everything before they write) - except for
+        # the sources of a post stage, which is evaluated AFTER r' has been parked in its destination slot
+        late = set(t[0] for t in o.post[0] + o.post[1] if t[0] is not None) if o.post else set()
+        dying = [v for v in protect if next_use(v, i + 1) == INF]
+        for v in dying:
+            if v not in late:
+                release(v)
+        dslot = []
+        keep = set(v for v in all_srcs if v in loc)
+        for v in dsts:
+            d = take_slot(i + 1, protect=keep)
+            loc[v] = d
+            slot_val[d] = v
+            keep = keep | {v}
+            dslot.append(d)
+        for v in dying:
+            if v in late:
+                release(v)
+        d = dslot[0] if dslot else 0
+        src_slots = [sl[v] for v in o.srcs]
+        if o.op in isa.PRODUCT_OPS:
+            imm = (o.canon[0] << isa.MUL_CANON_SHIFT) | (o.canon[1] << (isa.MUL_CANON_SHIFT + 2))
+            ext = bool(o.hi) or o.post is not None
+            if ext:
+                imm |= isa.MUL_EXT
+            d_r = dslot[0] if o.store_r else 0
+            if o.op == "MUL":
+                k = 0
+                a = src_slots[k]; k += 1
+                b = 0
+                if o.flags & isa.MUL_B:
+                    b = src_slots[k]; k += 1
+                c = src_slots[k]; k += 1
+                e = 0
+                if o.flags & isa.MUL_E:
+                    e = src_slots[k]; k += 1
+                emit("MUL", d=d_r, a=a, b=b, c=c, e=e, imm=imm | o.flags)
+            elif o.op == "SQR":
+                b = src_slots[1] if o.flags & isa.MUL_B else 0
+                emit("SQR", d=d_r, a=src_slots[0], b=b, imm=imm | o.flags)
+            else:
+                emit("MULFP", d=d_r, a=src_slots[0], b=src_slots[1], imm=imm | (isa.MULFP_HALF if o.imm else 0))
+            if ext:
+                d2 = dslot[-1] if o.dst2 is not None else 0
+                post = o.post or ([], [])
+                r_slot = d_r if o.store_r else d2
+
+                def enc(lst):
+                    return [isa.encode_entry(r_slot if leaf is None else sl[leaf], half, mult, neg) for leaf, half, mult, neg in lst]
+
+                pairs = isa.pair_entries(enc(post[0]), enc(post[1]), r_slot)
+                words.append(isa.encode_ext(d2, [(sl[v], neg) for v, neg in o.hi], o.store_r, len(pairs) // 2))
+                words.extend(isa.pack_entries(pairs))
+                stats["hi_terms"] += len(o.hi)
+                stats["post_stages"] += 1 if o.post else 0
+                stats["post_entries"] += len(post[0]) + len(post[1])
         elif o.op in ("INV", "DBL", "NEG", "CONJ", "MULXI"):
             emit(o.op, d=d, a=src_slots[0])
         elif o.op in ("ADD", "SUB"):
@@ -140,15 +177,18 @@ def allocate(ops, n_slots):
         elif o.op == "STG":
             emit("STG", d=o.f_lo, a=src_slots[0], b=o.f_hi, imm=o.imm)
         elif o.op == "LIN":
-            emit("LIN", d=d, a=len(o.terms), imm=o.K)
-            tw = [isa.encode_term(loc_s, xi, m0, m1) for loc_s, (_, xi, m0, m1) in zip(src_slots, o.terms)]
-            if len(tw) % 2:
-                tw.append(0)
-            for j in range(0, len(tw), 2):
-                words.append(tw[j] | (tw[j + 1] << 32))
+
+            def enc(lst):
+                return [isa.encode_entry(sl[leaf], half, mult, neg) for leaf, half, mult, neg in lst]
+
+            pairs = isa.pair_entries(enc(o.terms[0]), enc(o.terms[1]), src_slots[0])
+            emit("LIN", d=d, a=len(pairs) // 2)
+            words.extend(isa.pack_entries(pairs))
+            stats["lin_entries"] += len(o.terms[0]) + len(o.terms[1])
         else:
             raise ValueError(o.op)
-        if o.dst is not None and next_use(o.dst, i + 1) == INF:
-            release(o.dst)  # result never used
+        for v in dsts:
+            if next_use(v, i + 1) == INF:
+                release(v)  # result never used
     emit("END")
     return Allocated(words, n_slots, n_scratch, dict(stats))

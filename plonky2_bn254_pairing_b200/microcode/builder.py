@@ -155,14 +155,12 @@ class Builder:
     def stg(self, arr, f_lo, f_hi, v):
         self._emit("STG", [v], imm=arr, f_lo=f_lo, f_hi=f_hi, has_dst=False)
 
-    # ---- small multiples (canonical, via add chains; rare enough not to deserve an opcode yet)
+    # ---- small multiples: a linear pseudo-op that the fusion pass folds into whatever consumes it
     def times(self, a, k):
-        assert k >= 1
+        assert 1 <= k <= 31
         if k == 1:
             return a
-        if k % 2 == 0:
-            return self.times(a, k // 2).dbl()
-        return self.times(a, k - 1) + a
+        return self._emit("MULK", [a], imm=k)
 
     # ---- Fq12 load / store in MyFq12 coefficient order: coeffs[i] + coeffs[i+6] u  <->  w^i
     def ld_fq12(self, arr, base=0):
@@ -332,13 +330,11 @@ class Builder:
         # s * C^2 = xi c1 + c0 s
         sc0, sc1 = c1.mulxi(), c0
 
-        def three_minus_two(x, y):  # 3x - 2y
-            t = x - y
-            return t.dbl() + x
+        def three_minus_two(x, y):  # 3x - 2y   (x used once: the whole expression folds into x's product)
+            return self.times(x, 3) - y.dbl()
 
         def three_plus_two(x, y):  # 3x + 2y
-            t = x + y
-            return t.dbl() + x
+            return self.times(x, 3) + y.dbl()
 
         n0 = three_minus_two(a0, f[0])
         n3 = three_plus_two(a1, f[3])

@@ -1,20 +1,35 @@
-"""Fusion pass: SSA program of elementary Fq2 ops  ->  SSA program of MUL/SQR (with pre-additions), MULFP,
-INV, loads/stores and LIN (one variable-length linear-combination instruction).
+"""Fusion pass: SSA program of elementary Fq2 ops  ->  SSA program of product-class instructions
+(MUL / SQR / MULFP with pre-additions, hi terms and a post LIN stage), INV, loads/stores and the few linear
+instructions that could not be attached to a product.
 
-Why: measured on B200 (profiles/opbench_r1.txt) every elementary linear op (add, sub, double, neg, *xi)
-costs ~215 SM-sub-partition cycles per warp, independent of occupancy - it moves three 64-byte slots per
-thread through shared memory (128 B/clk/SM shared by four sub-partitions) and performs its own modular
-reduction.  Trees of linear ops with single-use intermediates are therefore collapsed into ONE instruction
-that reads each leaf once, accumulates lazily in registers (signed, unreduced) and reduces once.
+Why (measured on B200, profiles/): a stand-alone linear opcode costs ~250-450 sub-partition cycles, nearly all
+of it dispatch and shared-memory traffic (three 64-byte slot moves per thread at 128 B/clk/SM) for ~100 cycles
+of arithmetic, and the tower formulas contain ~2.6 of them per multiplication.  Almost every linear value in a
+pairing is `product +- older values` (Karatsuba recombination, v-multiplication, 3x-2y in the cyclotomic
+squaring, the Fq12-level even/odd halves), so it is computed in the epilogue of the product that completes it:
 
-Every Fq-linear map of an Fq2 value x = (x0, x1) is a 2x2 integer matrix; the pass tracks one matrix per
-leaf and finally decomposes  M = diag(p, q) + XI * diag(r, s),  XI = [[9,-1],[1,9]]  (always possible and
-unique), which is exactly what the kernel's LIN handler evaluates.
+  * hi terms   r' = redc(T + 2^256 * sum(+-s_i)):  canonical slots added into the upper half of the wide
+               product before the Montgomery reduction - eight adds per component, no extra reduction;
+  * post LIN   v = LIN(r', slots ...): a lazily accumulated linear combination (small integer coefficients,
+               optional xi = 9 + u factor) of r' - still in registers - and older slots, reduced once.
+
+Every Fq-linear map of an Fq2 value x = (x0, x1) is a 2x2 integer matrix; the pass tracks one matrix per leaf
+and decomposes  M = diag(p, q) + XI * diag(r, s),  XI = [[9,-1],[1,9]]  (always possible and unique), which is
+exactly what the kernel's LIN core evaluates.
+
+Range contracts (checked here for ALL inputs, the kernel does not check):
+  * wide values stay below 2^512 - p 2^256 = 4.29 p 2^256 so that redc's result fits eight limbs;
+  * the result bound selects the number of conditional subtractions (`canon` levels, per component);
+  * a LIN accumulator plus K p lies in [0, 1024 p).
 """
 from . import isa
 
-LINEAR = ("ADD", "SUB", "NEG", "DBL", "MULXI", "CONJ", "MOV")
+LINEAR = ("ADD", "SUB", "NEG", "DBL", "MULXI", "CONJ", "MOV", "MULK")
 I2 = (1, 0, 0, 1)
+NEG_I2 = (-1, 0, 0, -1)
+U = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47 / 2.0 ** 256   # p / 2^256
+WIDE_LIMIT = 2.0 ** 256 / 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47 - 1.0 - 1e-6
+MAX_SRCS = 10          # distinct source slots one instruction may name (slot budget is 14)
 
 
 def m_add(a, b):
@@ -41,39 +56,87 @@ def decompose(M):
 
 
 class FOp:
-    __slots__ = ("op", "dst", "srcs", "imm", "f_lo", "f_hi", "terms", "K", "flags")
+    __slots__ = ("op", "dst", "srcs", "imm", "f_lo", "f_hi", "terms", "K", "flags",
+                 "hi", "post", "dst2", "store_r", "canon")
 
     def __init__(self, op, dst, srcs, imm=0, f_lo=0, f_hi=0, terms=None, K=0, flags=0):
         self.op, self.dst, self.srcs, self.imm, self.f_lo, self.f_hi = op, dst, list(srcs), imm, f_lo, f_hi
-        self.terms, self.K, self.flags = terms, K, flags
+        self.terms, self.K, self.flags = terms, K, flags   # terms: (ent0, ent1) of a LIN
+        # product-class epilogue
+        self.hi = []          # [(value, negate)]
+        self.post = None      # (ent0, ent1); a leaf of None names r'
+        self.dst2 = None      # value produced by the post stage
+        self.store_r = False  # r' (= dst) is written to a slot (set by the first reader / the final fix-up)
+        self.canon = (0, 0)
+
+    def all_srcs(self):
+        s = list(self.srcs) + [v for v, _ in self.hi]
+        if self.post:
+            s += [t[0] for t in self.post[0] + self.post[1] if t[0] is not None]
+        return s
+
+    def dsts(self):
+        out = []
+        if self.dst is not None and (self.op not in isa.PRODUCT_OPS or self.store_r):
+            out.append(self.dst)
+        if self.dst2 is not None:
+            out.append(self.dst2)
+        return out
 
 
-def _terms_of(expr):
-    """expr: {leaf: M} -> (terms [(leaf, xi, m0, m1)], K, Ktot) or None if not encodable."""
-    terms = []
-    neg = [0, 0]
-    pos = [0, 0]
+def wide_bounds(op, flags):
+    """Upper bounds of (T0, T1) in units of p 2^256 for canonical slot inputs."""
+    if op == "MUL":
+        la = 2 if (flags & isa.MUL_B and not flags & isa.MUL_BCANON) else 1
+        lb = 2 if flags & isa.MUL_E else 1
+        return (1.0, 2 * la * lb * U)   # T0 = a0b0 - a1b1 (+ p 2^256 if negative) < p 2^256
+    if op == "SQR":
+        return (2 * U, 2 * U)
+    if op == "MULFP":
+        return (U, U)
+    raise ValueError(op)
+
+
+def canon_levels(op, flags, n_hi):
+    lv = []
+    for b in wide_bounds(op, flags):
+        tot = b + n_hi
+        assert tot < WIDE_LIMIT, "wide value out of range"
+        r_bound = tot + 1.0          # redc adds < p
+        lv.append(0 if r_bound <= 2.0 else 1 if r_bound <= 4.0 else 2)
+    return tuple(lv)
+
+
+def max_hi_terms(op, flags):
+    b = max(wide_bounds(op, flags))
+    n = 0
+    while n < 3 and b + n + 1 < WIDE_LIMIT:
+        n += 1
+    return n
+
+
+def entries_of(expr):
+    """expr: {leaf: M (2x2 integer matrix, row-major)} -> (ent0, ent1) or None if not encodable.
+    ent_c = [(leaf, half, mult, neg)]: output component c = sum of mult * (neg ? p - z : z), z = leaf[half]."""
+    ents = ([], [])
     for leaf, M in expr.items():
-        (p, q), (r, s) = decompose(M)
-        if max(abs(p), abs(q), abs(r), abs(s)) > isa.LIN_MAX_MULT:
+        for c in (0, 1):
+            for half in (0, 1):
+                k = M[2 * c + half]
+                if k == 0:
+                    continue
+                if abs(k) > isa.LIN_MAX_MULT:
+                    return None
+                ents[c].append((leaf, half, abs(k), k < 0))
+    for e in ents:
+        if len(e) > isa.LIN_MAX_ENT or sum(t[2] for t in e) > isa.LIN_MAX_SUM:
             return None
-        if p or q:
-            terms.append((leaf, False, p, q))
-            for c, m in ((0, p), (1, q)):
-                (neg if m < 0 else pos)[c] += abs(m)
-        if r or s:
-            terms.append((leaf, True, r, s))
-            # R0 += 9 r x0 - s x1 ; R1 += r x0 + 9 s x1
-            for c, m in ((0, 9 * r), (0, -s), (1, r), (1, 9 * s)):
-                (neg if m < 0 else pos)[c] += abs(m)
-    K = max(neg)
-    ktot = K + max(pos)
-    if len(terms) > isa.LIN_MAX_TERMS or K > isa.LIN_MAX_K or ktot > 1000:
-        return None
-    return terms, K, ktot
+    return ents
 
 
-def fuse(ops, enable=True, lin_trees=False):
+def fuse(ops, enable=True, attach=True, max_srcs=MAX_SRCS):
+    """enable=False: no fusion at all (every linear op stays elementary, no pre-additions) - the baseline
+    lowering the tests compare against.  attach=False: pre-additions and LIN trees only."""
     uses = {}
     user = {}
     defop = {}
@@ -90,12 +153,13 @@ def fuse(ops, enable=True, lin_trees=False):
             return False
         u = user[v]
         if u.op in LINEAR:
-            return lin_trees
+            return True
         return u.op in ("MUL", "SQR") and o.op in ("ADD", "SUB") and u.srcs.count(v) == 1
 
     out = []
     alias = {}
-    done = set()     # values materialised in `out`
+    pos = {}         # materialised value -> index in `out` of the instruction producing it
+    prim_of = {}     # value that is the r' of a product instruction -> that FOp
     pending = {}     # deferred linear value -> its Op
 
     def res(v):
@@ -103,14 +167,12 @@ def fuse(ops, enable=True, lin_trees=False):
             v = alias[v]
         return v
 
-    def expand(v, budget):
-        """Linear expression of v over materialised leaves: {leaf: M}.  Deferred children are inlined
-        while the result stays encodable; otherwise the child is materialised and becomes a leaf."""
+    def expand(v):
+        """Linear expression of v over materialised leaves: {leaf: M}."""
         v = res(v)
         if v not in pending:
             return {v: I2}
         o = pending[v]
-        parts = []
         if o.op == "ADD":
             parts = [(o.srcs[0], 1), (o.srcs[1], 1)]
         elif o.op == "SUB":
@@ -119,20 +181,20 @@ def fuse(ops, enable=True, lin_trees=False):
             parts = [(o.srcs[0], -1)]
         elif o.op == "DBL":
             parts = [(o.srcs[0], 2)]
-        elif o.op in ("MULXI", "CONJ", "MOV"):
+        elif o.op == "MULK":
+            parts = [(o.srcs[0], o.imm)]
+        else:  # MULXI, CONJ, MOV
             parts = [(o.srcs[0], 1)]
         expr = {}
         for src, k in parts:
-            sub = expand(src, budget)
-            for leaf, M in sub.items():
+            for leaf, M in expand(src).items():
                 M = m_scale(M, k)
                 expr[leaf] = m_add(expr[leaf], M) if leaf in expr else M
         if o.op == "MULXI":
             expr = {l: m_xi(M) for l, M in expr.items()}
         elif o.op == "CONJ":
             expr = {l: m_conj(M) for l, M in expr.items()}
-        expr = {l: M for l, M in expr.items() if any(M)}
-        return expr
+        return {l: M for l, M in expr.items() if any(M)}
 
     def consume(v):
         """Drop v and every deferred value inlined beneath it from `pending`."""
@@ -142,49 +204,135 @@ def fuse(ops, enable=True, lin_trees=False):
             if s in pending:
                 consume(s)
 
+    def touch(v):
+        """v is read from a slot by some instruction: its producer must store it."""
+        f = prim_of.get(v)
+        if f is not None:
+            f.store_r = True
+        return v
+
+    touched = set()
+
+    def touch_t(v):
+        touched.add(v)
+        return touch(v)
+
+    def try_attach(v, expr):
+        """Compute linear value v in the epilogue of the product instruction that completes it."""
+        if not attach or len(expr) < 1:
+            return False
+        leaves = list(expr)
+        if any(l not in pos for l in leaves):
+            return False
+        last = max(leaves, key=lambda l: pos[l])
+        f = prim_of.get(last)
+        if f is None or f.post is not None:
+            return False
+        k = pos[last]
+        others = [l for l in leaves if l is not last]
+        if any(pos[l] >= k for l in others):
+            return False
+        n_srcs = len(set(f.all_srcs()) | set(others))
+        if n_srcs > max_srcs:
+            return False
+        # hi terms: leaves whose matrix equals +-M_r ride through the Montgomery reduction with r
+        # (v = M_r (r +- s1 +- s2 +- s3) + rest); needs the raw r not to be wanted by anything else
+        Mr = expr[last]
+        negMr = m_scale(Mr, -1)
+        hi = []
+        flags = f.flags
+        if not f.hi and uses.get(last, 0) == 1 and last not in touched:
+            cand = [l for l in others if expr[l] in (Mr, negMr)]
+            room = max_hi_terms(f.op, flags)
+            if len(cand) > room and f.op == "MUL" and flags & isa.MUL_B:
+                # both operands are lazy sums: canonicalising the first one (one conditional subtraction
+                # per component) makes room for a third hi term
+                if max_hi_terms(f.op, flags | isa.MUL_BCANON) > room:
+                    flags |= isa.MUL_BCANON
+                    room = max_hi_terms(f.op, flags)
+            hi = [(l, expr[l] == negMr) for l in cand[:room]]
+        rest = {l: expr[l] for l in others if l not in [h[0] for h in hi]}
+        if not rest and Mr == I2:
+            post = None
+        else:
+            pexpr = dict(rest)
+            pexpr[None] = Mr
+            post = entries_of(pexpr)
+            if post is None:
+                return False
+        if hi:
+            f.flags = flags
+            f.hi = hi
+            f.canon = canon_levels(f.op, f.flags, len(hi))
+            del prim_of[last]
+            del pos[last]
+            if post is None:
+                f.dst = v               # v itself is the hi-form value
+                prim_of[v] = f
+                pos[v] = k
+                f.store_r = False       # set by the first reader (touch) or by the end-of-pass fix-up
+                for l, _ in hi:
+                    touch_t(l)
+                return True
+            f.dst = ("hi", last)        # r' exists only inside this instruction
+            last = f.dst
+            pos[last] = k
+        f.post = post
+        f.dst2 = v
+        f.store_r = last in touched
+        for l in others:
+            touch_t(l)
+        pos[v] = k
+        return True
+
     def emit_lin(v):
         """Materialise linear value v (removing it from pending)."""
         v = res(v)
         o = pending[v]
-        if not lin_trees:
-            # elementary form: one dedicated opcode per modular step
+        if not enable:
             pending.pop(v)
-            if o.op == "MOV":
-                alias[v] = need(o.srcs[0])
-                return
-            out.append(FOp(o.op, v, [need(s) for s in o.srcs]))
-            done.add(v)
+            if o.op == "MULK":
+                src = need(o.srcs[0])
+                out.append(FOp("LIN", v, [src], terms=([(src, 0, o.imm, False)], [(src, 1, o.imm, False)])))
+            else:
+                out.append(FOp(o.op, v, [need(s) for s in o.srcs]))
+            pos[v] = len(out) - 1
             return
-        expr = expand(v, None)
-        enc = _terms_of(expr) if expr else None
-        if expr and enc is None:
-            # too big: materialise deferred children one at a time (largest first) and retry
+        expr = expand(v)
+        assert expr, "zero linear expression"
+        if len(expr) == 1:
+            (leaf, M), = expr.items()
+            if M == I2:
+                consume(v)
+                alias[v] = leaf
+                return
+        if try_attach(v, expr):
+            consume(v)
+            return
+        enc = entries_of(expr)
+        if enc is None or len(expr) > max_srcs:
+            # too big: materialise deferred children one at a time and retry
             kids = [res(s) for s in o.srcs if res(s) in pending]
             assert kids, "single linear op not encodable"
-            for k in kids:
-                emit_lin(k)
-                expr = expand(v, None)
-                enc = _terms_of(expr)
-                if enc is not None:
-                    break
-            assert enc is not None
+            for kid in kids:
+                emit_lin(kid)
+            return emit_lin(v)
         consume(v)
-        if not expr:
-            # identically zero: load the constant instead (never happens in the shipped programs)
-            raise AssertionError("zero linear expression")
-        terms, K, _ = enc
-        if len(terms) == 1 and terms[0][1:] == (False, 1, 1):
-            alias[v] = terms[0][0]
-            return
-        out.append(FOp("LIN", v, [t[0] for t in terms], terms=terms, K=K))
-        done.add(v)
+        # single elementary operation on one or two slots: use the dedicated opcode
+        elem = _as_elementary(expr)
+        if elem is not None:
+            opname, srcs = elem
+            out.append(FOp(opname, v, [touch_t(s) for s in srcs]))
+        else:
+            out.append(FOp("LIN", v, [touch_t(l) for l in expr], terms=enc))
+        pos[v] = len(out) - 1
 
     def need(v):
         v = res(v)
         if v in pending:
             emit_lin(v)
             v = res(v)
-        return v
+        return touch_t(v)
 
     for o in ops:
         if o.op in LINEAR:
@@ -215,12 +363,49 @@ def fuse(ops, enable=True, lin_trees=False):
                 if e is not None:
                     flags |= isa.MUL_E | (isa.MUL_ENEG if en else 0)
                     srcs.append(e)
-            out.append(FOp(o.op, o.dst, srcs, flags=flags))
-            done.add(o.dst)
+            f = FOp(o.op, o.dst, srcs, flags=flags)
+            f.canon = canon_levels(o.op, flags, 0)
+            out.append(f)
+            pos[o.dst] = len(out) - 1
+            prim_of[o.dst] = f
             continue
         srcs = [need(s) for s in o.srcs]
-        out.append(FOp(o.op, o.dst, srcs, imm=o.imm, f_lo=o.f_lo, f_hi=o.f_hi))
+        f = FOp(o.op, o.dst, srcs, imm=o.imm, f_lo=o.f_lo, f_hi=o.f_hi)
+        if o.op == "MULFP":
+            f.canon = canon_levels("MULFP", 0, 0)
+            prim_of[o.dst] = f
+        out.append(f)
         if o.dst is not None:
-            done.add(o.dst)
+            pos[o.dst] = len(out) - 1
     assert not pending, "dangling deferred values"
+    for f in out:
+        if f.op in isa.PRODUCT_OPS and f.post is None:
+            f.store_r = True   # a product without a post stage always writes its result
+        if f.op in isa.PRODUCT_OPS and f.post is not None and not f.store_r:
+            assert f.dst2 is not None
     return out
+
+
+def _as_elementary(expr):
+    """{leaf: M} -> (opcode, [srcs]) when the expression is exactly one elementary linear operation."""
+    items = list(expr.items())
+    if len(items) == 1:
+        (a, M), = items
+        if M == (2, 0, 0, 2):
+            return "DBL", [a]
+        if M == NEG_I2:
+            return "NEG", [a]
+        if M == (1, 0, 0, -1):
+            return "CONJ", [a]
+        if M == m_xi(I2):
+            return "MULXI", [a]
+        return None
+    if len(items) == 2:
+        (a, Ma), (b, Mb) = items
+        if Ma == I2 and Mb == I2:
+            return "ADD", [a, b]
+        if Ma == I2 and Mb == NEG_I2:
+            return "SUB", [a, b]
+        if Ma == NEG_I2 and Mb == I2:
+            return "SUB", [b, a]
+    return None

@@ -29,70 +29,81 @@ def _pre(slots, a, b, has_b, neg_b):
     return x
 
 
-def lin_eval(terms, K, values):
-    """terms: [(xi, m0, m1)], values: [(x0, x1)] canonical.  Returns the Fq2 result and checks the
-    kernel's contract: with every input in [0, p) the lazy sum + K*p lies in [0, 1024 p)."""
-    a0 = a1 = x0 = x1 = 0
-    for (xi, m0, m1), v in zip(terms, values):
-        assert 0 <= v[0] < P and 0 <= v[1] < P
-        if xi:
-            x0 += m0 * v[0]
-            x1 += m1 * v[1]
-        else:
-            a0 += m0 * v[0]
-            a1 += m1 * v[1]
-    r0 = a0 + 9 * x0 - x1 + K * P
-    r1 = a1 + x0 + 9 * x1 + K * P
-    assert 0 <= r0 < 1024 * P and 0 <= r1 < 1024 * P, "LIN lazy-accumulation contract violated"
-    return (r0 % P, r1 % P)
+def lin_eval(ents, slots):
+    """One output component of a LIN: sum of mult * (neg ? p - z : z).  Checks the kernel's contract
+    (canonical inputs, the lazy sum stays below 1024 p - true for ALL inputs because it only depends on
+    the multipliers)."""
+    assert sum(m for _, _, m, _ in ents) <= isa.LIN_MAX_SUM and len(ents) <= isa.LIN_MAX_ENT
+    acc = 0
+    for slot, half, mult, neg in ents:
+        if mult == 0:
+            assert slots[slot] is not None  # padding entry: the kernel still loads the slot
+            continue
+        z = slots[slot][half]
+        assert 0 <= z < P
+        acc += mult * ((P - z) if neg else z)
+    return acc % P
 
 
-def lin_worst_case_ok(terms, K):
-    """Static check of the same contract for ALL inputs in [0,p): evaluate at the extreme points."""
-    lo = [0, 0]
-    hi = [0, 0]
-    for xi, m0, m1 in terms:
-        contrib = ((0, 9 * m0), (0, -m1), (1, m0), (1, 9 * m1)) if xi else ((0, m0), (1, m1))
-        for c, m in contrib:
-            if m < 0:
-                lo[c] += m
-            else:
-                hi[c] += m
-    return all(lo[c] + K >= 0 and hi[c] + K < 1024 for c in (0, 1))
+def _lin(ins, slots):
+    return (lin_eval(ins.ent0, slots), lin_eval(ins.ent1, slots))
+
+
+# wide-value range contract of the product-class epilogue, in exact integers
+_WIDE_MAX = (1 << 512) - (P << 256)
 
 
 def run(words, consts, arrays, n_slots, n_scratch):
     """arrays: {arr_id: list of Fq ints}; STG writes into arrays[arr_id] (a dict or list)."""
     slots = [None] * n_slots
     scratch = [None] * max(n_scratch, 1)
-    pc = 0
-    while True:
-        op, d, a, b, c, e, imm = isa.decode(words[pc])
-        pc += 1
+    for ins in isa.parse(words):
+        op, d, a, b, c, e, imm = ins.op, ins.d, ins.a, ins.b, ins.c, ins.e, ins.imm
         if op == "END":
             break
-        if op == "MUL":
-            x = _pre(slots, a, b, imm & isa.MUL_B, imm & isa.MUL_BNEG)
-            y = _pre(slots, c, e, imm & isa.MUL_E, imm & isa.MUL_ENEG)
-            slots[d] = ((x[0] * y[0] - x[1] * y[1]) % P, (x[0] * y[1] + x[1] * y[0]) % P)
-        elif op == "SQR":
-            x = _pre(slots, a, b, imm & isa.MUL_B, imm & isa.MUL_BNEG)
-            slots[d] = ((x[0] * x[0] - x[1] * x[1]) % P, 2 * x[0] * x[1] % P)
-        elif op == "MULFP":
-            x, s = slots[a], slots[b][imm & 1]
-            slots[d] = (x[0] * s % P, x[1] * s % P)
+        if op in isa.PRODUCT_OPS:
+            # mirror the kernel's unreduced arithmetic closely enough to check its range contract
+            if op == "MUL":
+                x, y = slots[a], slots[c]
+                if imm & isa.MUL_B:
+                    t = slots[b]
+                    x = (x[0] - t[0] + P, x[1] - t[1] + P) if imm & isa.MUL_BNEG else (x[0] + t[0], x[1] + t[1])
+                    if imm & isa.MUL_BCANON:
+                        x = (x[0] % P, x[1] % P)
+                if imm & isa.MUL_E:
+                    t = slots[e]
+                    y = (y[0] - t[0] + P, y[1] - t[1] + P) if imm & isa.MUL_ENEG else (y[0] + t[0], y[1] + t[1])
+                T0 = x[0] * y[0] - x[1] * y[1]
+                if T0 < 0:
+                    T0 += P << 256
+                T1 = x[0] * y[1] + x[1] * y[0]
+            elif op == "SQR":
+                x = _pre(slots, a, b, imm & isa.MUL_B, imm & isa.MUL_BNEG)
+                T0 = (x[0] + x[1]) * ((x[0] - x[1]) % P)
+                T1 = 2 * x[0] * x[1]
+            else:
+                x, s = slots[a], slots[b][1 if imm & isa.MULFP_HALF else 0]
+                T0, T1 = x[0] * s, x[1] * s
+            # hi terms: on the device (Montgomery domain) h * 2^256 is added to the wide value, which adds h to
+            # the reduced result; in this plain-residue model the value gets h and the range check gets h * 2^256
+            H0 = H1 = 0
+            for slot, neg in ins.hi:
+                h = slots[slot]
+                assert 0 <= h[0] < P and 0 <= h[1] < P
+                H0 += (P - h[0]) if neg else h[0]
+                H1 += (P - h[1]) if neg else h[1]
+            lv0, lv1 = (imm >> isa.MUL_CANON_SHIFT) & 3, (imm >> (isa.MUL_CANON_SHIFT + 2)) & 3
+            for T, lv in ((T0 + (H0 << 256), lv0), (T1 + (H1 << 256), lv1)):
+                assert 0 <= T < _WIDE_MAX, "wide value out of range"
+                # redc gives T / 2^256 + (< p); the canon ladder handles [0, 2p (lv + 1))
+                assert (T >> 256) + P < 2 * P * (lv + 1), "canon level too small"
+            r = ((T0 + H0) % P, (T1 + H1) % P)
+            # the kernel parks r' in its slot (d, or d2 when r' is not wanted for itself), then runs the post LIN
+            slots[ins.r_slot()] = r
+            if ins.has_post():
+                slots[ins.d2] = _lin(ins, slots)
         elif op == "LIN":
-            nterms, K = a, imm
-            terms, vals = [], []
-            for j in range(nterms):
-                w = words[pc + j // 2]
-                t = (w >> (32 * (j % 2))) & 0xFFFFFFFF
-                slot, xi, m0, m1 = isa.decode_term(t)
-                terms.append((xi, m0, m1))
-                vals.append(slots[slot])
-            pc += (nterms + 1) // 2
-            assert lin_worst_case_ok(terms, K), "LIN K too small / range too large"
-            slots[d] = lin_eval(terms, K, vals)
+            slots[d] = _lin(ins, slots)
         elif op == "LDC":
             slots[d] = consts[imm]
         elif op == "LDG":
@@ -126,26 +137,14 @@ def run(words, consts, arrays, n_slots, n_scratch):
 
 
 def walk(words):
-    """Yield (opname, n_slot_moves) per instruction, skipping LIN term words."""
-    pc = 0
-    while pc < len(words):
-        op, d, a, b, c, e, imm = isa.decode(words[pc])
-        pc += 1
-        if op == "LIN":
-            pc += (a + 1) // 2
-            yield op, a + 1
-        elif op == "MUL":
-            yield op, 3 + bool(imm & isa.MUL_B) + bool(imm & isa.MUL_E)
-        elif op == "SQR":
-            yield op, 2 + bool(imm & isa.MUL_B)
-        elif op == "MULFP":
-            yield op, 2.5
-        elif op == "END":
-            yield op, 0
-            break
-        else:
-            yield op, {"LDC": 1, "LDG": 1, "STG": 1, "SPILL": 1, "FILL": 1, "INV": 2, "ADD": 3, "SUB": 3, "DBL": 2,
-                       "NEG": 2, "CONJ": 2, "MULXI": 2}[op]
+    """Yield (opname, n_slot_moves) per instruction (a LIN entry moves half a slot)."""
+    for ins in isa.parse(words):
+        if ins.op in ("LDC", "LDG", "FILL"):
+            yield ins.op, 1
+            continue
+        nent = len(ins.ent0) + len(ins.ent1)
+        full_reads = len(ins.slots_read()) - nent
+        yield ins.op, full_reads + 0.5 * nent + len(ins.slots_written()) + (1 if ins.has_post() and not ins.store_r else 0)
 
 
 def work(words):

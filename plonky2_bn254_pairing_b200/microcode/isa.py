@@ -15,14 +15,27 @@ flow is uniform across the grid.  One instruction word is 64 bits, eight byte-wi
 MUL / SQR take optional pre-additions (Karatsuba operands are sums of two slots):
     MUL  d = (a [+-b]) * (c [+-e])     imm bit0: b present, bit1: b subtracted, bit2: e present, bit3: e subtracted
     SQR  d = (a [+-b])^2               imm bit0: b present, bit1: b subtracted
+MUL / SQR / MULFP (the "product class") share one epilogue, which is where most linear work of the tower
+lives (measured: a stand-alone linear opcode costs ~250 sub-partition cycles, all of it shared-memory
+traffic and dispatch, against ~100 cycles of arithmetic):
+    T   = wide (512-bit, unreduced) product of the operands
+    T  += 2^256 * sum(+-S[h_i])        up to three "hi terms": canonical slots added into the upper half
+                                       of T before the Montgomery reduction, so r' picks them up for free
+    r'  = canon(redc(T))               imm bits 5-6: number of extra conditional subtractions (bound / 2p)
+    S[d]  = r'                         (skipped when only the post value is wanted)
+    S[d2] = LIN(r', slots ...)         optional post stage: a LIN expression that may read r' (it is parked in
+                                       slot d, or in d2 when it is not wanted for itself)
+imm bit 4 (EXT) says an extension word follows:
+    byte 0 d2, bytes 1-3 h1 h2 h3, byte 4 hflags (bits0-1 number of hi terms, bits 2-4 negate h1..h3,
+    bit 7 store r' to d as well as the post value to d2), byte 5 = number of entry pairs of the post LIN;
+then ceil(pairs / 2) words of 16-bit LIN entries.
 ADD / SUB / DBL / NEG / CONJ / MULXI are the elementary linear opcodes (one modular step each).
-LIN is an optional fused form (kept for experiments; measured slower on B200 than the elementary ops,
-see DESIGN.md section 6): a variable-length instruction
-    d = sum_i diag(m0_i, m1_i) * x_i  +  xi * sum_j diag(m0_j, m1_j) * x_j        (xi = 9 + u)
-with small signed integer multipliers per Fq component (this subsumes add, sub, neg, double, conj,
-multiplication by xi and by small constants).  Header word: d, a = number of terms, imm = K (the
-multiple of p that makes the lazily accumulated value non-negative); each following word carries
-two 32-bit term descriptors: [slot:8][flags:8][m0:int8][m1:int8], flags bit0 = term belongs to the xi sum.
+LIN is the general linear instruction: each of the two output components is a lazily accumulated sum
+    out_c = sum_j mult_j * z_j,   z_j = one Fq half of a slot, or p minus it,   1 <= mult_j <= 31
+(this subsumes add, sub, neg, double, conj, multiplication by xi = 9 + u and by small constants), reduced once by a
+quotient estimate.  Every entry is one 8-MAC IMAD.WIDE chain into a 64-bit-column accumulator - the accumulation
+costs no ALU instructions.  Entries come in (component 0, component 1) pairs; header word: d, a = number of pairs;
+entries follow, two pairs per word: [slot:8][half:1][neg:1][mult:6].
 
 `emit_c_defines()` writes the opcode numbers into the generated header so the CUDA side cannot drift.
 """
@@ -31,7 +44,7 @@ OPS = [
     "END",    # stop
     "MUL",    # d = (a [+-b]) * (c [+-e])
     "SQR",    # d = (a [+-b])^2
-    "MULFP",  # d = a * s, s = c0 (imm=0) or c1 (imm=1) half of slot b, an Fq scalar
+    "MULFP",  # d = a * s, s = c0 or c1 (imm bit 15) half of slot b, an Fq scalar
     "LIN",    # d = linear combination (variable length, see above)
     "LDC",    # d = const[imm]
     "LDG",    # d = (arr[imm][a], arr[imm][b])   two Fq of this thread's element of global array imm
@@ -56,10 +69,15 @@ ARR_OUT = 3   # [12 Fq][n]   MyFq12 output
 ARR_AUX = 4   # second input array (program specific)
 
 MUL_B, MUL_BNEG, MUL_E, MUL_ENEG = 1, 2, 4, 8
-LIN_XI = 1
-LIN_MAX_TERMS = 8
+MUL_EXT = 16            # an extension word follows
+MUL_BCANON = 0x200      # MUL: canonicalise the (a +- b) operand (makes room for a third hi term)
+MUL_CANON_SHIFT = 5     # imm bits 5-6: extra conditional subtractions (0: r' < 2p, 1: < 4p, 2: < 6p)
+EXT_STORE_R = 0x80
+MULFP_HALF = 0x8000     # MULFP: the scalar is the c1 half of slot b
+PRODUCT_OPS = ("MUL", "SQR", "MULFP")
+LIN_MAX_ENT = 15    # entry pairs per LIN
 LIN_MAX_MULT = 31
-LIN_MAX_K = 63      # size of the K*p table in the kernel
+LIN_MAX_SUM = 1000  # sum of the multipliers of one component: the lazy value stays below 1024 p
 
 
 def encode(op, d=0, a=0, b=0, c=0, e=0, imm=0):
@@ -74,21 +92,127 @@ def decode(word):
             (word >> 40) & 0xFF, (word >> 48) & 0xFFFF)
 
 
-def encode_term(slot, xi, m0, m1):
-    assert 0 <= slot <= 0xFF and -LIN_MAX_MULT <= m0 <= LIN_MAX_MULT and -LIN_MAX_MULT <= m1 <= LIN_MAX_MULT
-    return slot | ((LIN_XI if xi else 0) << 8) | ((m0 & 0xFF) << 16) | ((m1 & 0xFF) << 24)
+def encode_ext(d2, hi, store_r, npairs):
+    """hi: list of (slot, negate); npairs: LIN entry pairs of the post stage."""
+    assert len(hi) <= 3 and 0 <= d2 <= 0xFF and 0 <= npairs <= LIN_MAX_ENT
+    w = d2
+    hflags = len(hi)
+    for i, (slot, neg) in enumerate(hi):
+        assert 0 <= slot <= 0xFF
+        w |= slot << (8 * (i + 1))
+        if neg:
+            hflags |= 4 << i
+    if store_r:
+        hflags |= EXT_STORE_R
+    return w | (hflags << 32) | (npairs << 40)
 
 
-def decode_term(t):
-    def s8(v):
-        return v - 256 if v >= 128 else v
+def decode_ext(w):
+    hflags = (w >> 32) & 0xFF
+    n = hflags & 3
+    hi = [((w >> (8 * (i + 1))) & 0xFF, bool(hflags & (4 << i))) for i in range(n)]
+    return w & 0xFF, hi, bool(hflags & EXT_STORE_R), (w >> 40) & 0xFF
 
-    return (t & 0xFF, bool((t >> 8) & LIN_XI), s8((t >> 16) & 0xFF), s8((t >> 24) & 0xFF))
+
+# LIN entry (16 bits): out_component += (neg ? p - z : z) * mult,  z = half `half` (0: c0, 1: c1) of slot `slot`
+def encode_entry(slot, half, mult, neg):
+    assert 0 <= slot <= 0xFF and half in (0, 1) and 0 <= mult <= LIN_MAX_MULT
+    return slot | (half << 8) | ((1 if neg else 0) << 9) | (mult << 10)
+
+
+def decode_entry(t):
+    return (t & 0xFF, (t >> 8) & 1, (t >> 10) & 63, bool((t >> 9) & 1))
+
+
+def pair_entries(ent0, ent1, pad_slot):
+    """Interleave the two components' entry lists into (comp0, comp1) pairs; the shorter list is padded with
+    multiplier-0 entries (they read `pad_slot`, any valid slot)."""
+    n = max(len(ent0), len(ent1))
+    pad = encode_entry(pad_slot, 0, 0, False)
+    out = []
+    for j in range(n):
+        out.append(ent0[j] if j < len(ent0) else pad)
+        out.append(ent1[j] if j < len(ent1) else pad)
+    return out
+
+
+def pack_entries(ents):
+    """16-bit entries -> 64-bit words, four (two pairs) per word."""
+    words = []
+    for j in range(0, len(ents), 4):
+        w = 0
+        for k, t in enumerate(ents[j:j + 4]):
+            w |= t << (16 * k)
+        words.append(w)
+    return words
+
+
+class Ins:
+    """One decoded instruction (with its extension / entry words)."""
+    __slots__ = ("op", "d", "a", "b", "c", "e", "imm", "d2", "hi", "store_r", "ent0", "ent1", "nwords")
+
+    def has_post(self):
+        return bool(self.ent0 or self.ent1)
+
+    def r_slot(self):
+        """Slot that holds r' while a post stage runs."""
+        return self.d if self.store_r else self.d2
+
+    def slots_read(self):
+        """Slot numbers the instruction reads (for range checks)."""
+        r = []
+        if self.op == "MUL":
+            r = [self.a, self.c] + ([self.b] if self.imm & MUL_B else []) + ([self.e] if self.imm & MUL_E else [])
+        elif self.op == "SQR":
+            r = [self.a] + ([self.b] if self.imm & MUL_B else [])
+        elif self.op in ("MULFP", "ADD", "SUB"):
+            r = [self.a, self.b]
+        elif self.op in ("INV", "DBL", "NEG", "CONJ", "MULXI", "STG", "SPILL"):
+            r = [self.a]
+        r += [s for s, _ in self.hi]
+        r += [t[0] for t in self.ent0 + self.ent1]
+        return r
+
+    def slots_written(self):
+        if self.op in PRODUCT_OPS:
+            w = [self.d] if self.store_r else []
+            return w + ([self.d2] if self.has_post() else [])
+        if self.op in ("STG", "SPILL", "END"):
+            return []
+        return [self.d]
+
+
+def parse(words):
+    """Iterate over the instructions of a program (stops after END)."""
+    pc = 0
+    while pc < len(words):
+        i = Ins()
+        i.op, i.d, i.a, i.b, i.c, i.e, i.imm = decode(words[pc])
+        start = pc
+        pc += 1
+        i.d2, i.hi, i.store_r, i.ent0, i.ent1 = 0, [], True, [], []
+        npairs = 0
+        if i.op in PRODUCT_OPS and i.imm & MUL_EXT:
+            i.d2, i.hi, st, npairs = decode_ext(words[pc])
+            pc += 1
+            i.store_r = st or npairs == 0
+        elif i.op == "LIN":
+            npairs = i.a
+        ents = []
+        for j in range(2 * npairs):
+            ents.append(decode_entry((words[pc + j // 4] >> (16 * (j % 4))) & 0xFFFF))
+        i.ent0, i.ent1 = ents[0::2], ents[1::2]
+        pc += (npairs + 1) // 2
+        i.nwords = pc - start
+        yield i
+        if i.op == "END":
+            return
 
 
 def emit_c_defines():
     s = "".join("#define BNP_OP_%s %d\n" % (name, i) for i, name in enumerate(OPS))
     s += "#define BNP_MUL_B %d\n#define BNP_MUL_BNEG %d\n#define BNP_MUL_E %d\n#define BNP_MUL_ENEG %d\n" % (
         MUL_B, MUL_BNEG, MUL_E, MUL_ENEG)
-    s += "#define BNP_LIN_XI %d\n#define BNP_LIN_MAX_K %d\n" % (LIN_XI, LIN_MAX_K)
+    s += "#define BNP_MUL_EXT %d\n#define BNP_MUL_CANON_SHIFT %d\n#define BNP_EXT_STORE_R %d\n#define BNP_MULFP_HALF %d\n#define BNP_MUL_BCANON %d\n" % (
+        MUL_EXT, MUL_CANON_SHIFT, EXT_STORE_R, MULFP_HALF, MUL_BCANON)
     return s

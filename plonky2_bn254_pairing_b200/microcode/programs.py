@@ -305,7 +305,7 @@ def prog_fq12_mul(b):
     b.st_fq12(isa.ARR_OUT, b.fq12_mul(b.ld_fq12(isa.ARR_F12), b.ld_fq12(isa.ARR_AUX)))
 
 
-OPTEST_OUTPUTS = 24
+OPTEST_OUTPUTS = 36
 
 
 def prog_optest(b):
@@ -323,7 +323,21 @@ def prog_optest(b):
         (x[2] - x[3]).dbl() + x[2],
         x[0].conj() + x[1].mulxi() - x[2].dbl(),
         b.times(x[5], 12) - x[4].conj(),
+        # product-class epilogues: hi terms (1, 2 and 3 of them, lazy and canonical operands), post LIN with and
+        # without xi, r' stored next to the post value, SQR / MULFP producers
+        x[0] * x[1] - x[2],
+        (x[0] + x[1]) * (x[2] + x[3]) - x[4] - x[5],
+        (x[0] + x[1]) * (x[2] + x[3]) - x[4] - x[5] + x[0],
+        x[2] * x[3] + x[0] - x[1] + x[5],
+        x[4] + (x[0] * x[5] - x[1] - x[2]).mulxi(),
+        (x[1] + x[2]) * (x[3] - x[4]) - x[0] - x[5] + x[2].mulxi(),
+        b.times(x[3].sqr(), 3) - x[4].dbl(),
+        b.times((x[0] + x[1]).sqr() - x[2] - x[3], 3) + x[5].dbl(),
+        x[1].mulfp(x[2], 1) - x[3] + x[4],
+        (x[0] - x[1]) * x[2] - x[3] - x[4] - x[5],
     ]
+    hp = x[1] * x[4] - x[0] - x[2]          # hi-form value with two readers: stored AND fed to a post stage
+    outs += [hp, x[3] + hp.mulxi()]
     assert len(outs) == OPTEST_OUTPUTS
     for i, v in enumerate(outs):
         b.stg(isa.ARR_OUT, 2 * i, 2 * i + 1, v)
@@ -357,6 +371,21 @@ def prog_opbench(b, op, count=2048):
             r = a + (c - vals[(i + 2) % 6] - vals[(i + 3) % 6]).mulxi()
         elif op == "MULS":
             r = (a + c) * (vals[(i + 2) % 6] + vals[(i + 3) % 6])
+        elif op == "MIX":
+            # the pairing's opcode proportions (MUL 4 : SQR 2 : ADD/SUB 12 : MULXI 2 : DBL 2), on six slots
+            k = i % 22
+            if k < 4:
+                r = a * c
+            elif k < 6:
+                r = a.sqr()
+            elif k < 12:
+                r = a + c
+            elif k < 18:
+                r = a - c
+            elif k < 20:
+                r = a.mulxi()
+            else:
+                r = a.dbl()
         else:
             raise ValueError(op)
         vals[i % 6] = r
@@ -373,7 +402,7 @@ PROGRAMS = [
     ("pairing_v1", prog_pairing, {"variant": 1}),
     ("fq12_mul", prog_fq12_mul, {}),
     ("optest", prog_optest, {}),
-] + [("opbench_" + o.lower(), prog_opbench, {"op": o}) for o in ("MUL", "SQR", "MULFP", "ADD", "SUB", "DBL", "NEG", "MULXI", "LIN4", "LIN4XI", "MULS")] \
+] + [("opbench_" + o.lower(), prog_opbench, {"op": o}) for o in ("MUL", "SQR", "MULFP", "ADD", "SUB", "DBL", "NEG", "MULXI", "LIN4", "LIN4XI", "MULS", "MIX")] \
   + [("frobenius_%d" % k, prog_frobenius, {"power": k}) for k in range(12)] \
   + [("miller_x%d" % k, prog_miller, {"n_pairs": k}) for k in (2, 3, 4)] \
   + [("pairing_x%d_v%d" % (k, v), prog_pairing, {"variant": v, "n_pairs": k}) for k in (2, 3, 4) for v in (0, 1)]

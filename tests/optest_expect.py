@@ -4,7 +4,9 @@ import bn254_oracle as O
 
 NAMES = ["MUL", "SQR", "MULFP0", "MULFP1", "ADD", "SUB", "NEG", "CONJ", "MULXI", "DBL", "INV", "MULC",
          "(a+b)(c+e)", "(a-b)(c-e)", "(a+b)c", "a(c-e)", "(a+b)^2", "(a-b)^2",
-         "a-b-c+d", "a+xi(b-c-d)", "27a-xi b", "3a-2b", "conj(a)+xi b-2c", "12a-conj(b)"]
+         "a-b-c+d", "a+xi(b-c-d)", "27a-xi b", "3a-2b", "conj(a)+xi b-2c", "12a-conj(b)",
+         "ab-c", "(a+b)(c+d)-e-f", "(a+b)(c+d)-e-f+a", "cd+a-b+f", "e+xi(af-b-c)", "(b+c)(d-e)-a-f+xi c",
+         "3d^2-2e", "3((a+b)^2-c-d)+2f", "b*c1-d+e", "(a-b)c-d-e-f", "be-a-c", "d+xi(be-a-c)"]
 
 
 def times(x, k):
@@ -30,6 +32,18 @@ def expected(row):
         sub(times(x[2], 3), times(x[3], 2)),
         sub(add(O.conjugate_fp2(x[0]), xi(x[1])), times(x[2], 2)),
         sub(times(x[5], 12), O.conjugate_fp2(x[4])),
+        sub(mul(x[0], x[1]), x[2]),
+        sub(sub(mul(add(x[0], x[1]), add(x[2], x[3])), x[4]), x[5]),
+        add(sub(sub(mul(add(x[0], x[1]), add(x[2], x[3])), x[4]), x[5]), x[0]),
+        add(sub(add(mul(x[2], x[3]), x[0]), x[1]), x[5]),
+        add(x[4], xi(sub(sub(mul(x[0], x[5]), x[1]), x[2]))),
+        add(sub(sub(mul(add(x[1], x[2]), sub(x[3], x[4])), x[0]), x[5]), xi(x[2])),
+        sub(times(O.fq2_sqr(x[3]), 3), times(x[4], 2)),
+        add(times(sub(sub(O.fq2_sqr(add(x[0], x[1])), x[2]), x[3]), 3), times(x[5], 2)),
+        add(sub(mul(x[1], (x[2][1], 0)), x[3]), x[4]),
+        sub(sub(sub(mul(sub(x[0], x[1]), x[2]), x[3]), x[4]), x[5]),
+        sub(sub(mul(x[1], x[4]), x[0]), x[2]),
+        add(x[3], xi(sub(sub(mul(x[1], x[4]), x[0]), x[2]))),
     ]
 
 

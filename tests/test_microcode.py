@@ -14,30 +14,20 @@ def run(name, arrays, n_slots):
     b = programs.build_program(name, pool)
     from plonky2_bn254_pairing_b200.microcode import fuse
     al = alloc.allocate(fuse.fuse(b.ops), n_slots)
-    pc = 0
-    while pc < len(al.words):  # every operand field within the slot budget
-        op, d, a, bb, c, e, imm = isa.decode(al.words[pc])
-        pc += 1
-        if op == "MUL":
-            assert max(d, a, bb, c, e) < n_slots
-        elif op in ("SQR", "MULFP"):
-            assert max(d, a, bb) < n_slots
-        elif op in ("INV", "DBL", "NEG", "CONJ", "MULXI"):
-            assert max(d, a) < n_slots
-        elif op in ("ADD", "SUB"):
-            assert max(d, a, bb) < n_slots
-        elif op == "SPILL":
-            assert a < n_slots and imm < max(al.n_scratch, 1)
-        elif op == "FILL":
-            assert d < n_slots and imm < al.n_scratch
-        elif op == "LIN":
-            assert d < n_slots and 1 <= a <= isa.LIN_MAX_TERMS and imm <= isa.LIN_MAX_K
-            for j in range(a):
-                t = (al.words[pc + j // 2] >> (32 * (j % 2))) & 0xFFFFFFFF
-                assert isa.decode_term(t)[0] < n_slots
-            pc += (a + 1) // 2
-        elif op == "END":
-            break
+    for ins in isa.parse(al.words):  # every operand field within the slot budget
+        for sl in ins.slots_read() + ins.slots_written():
+            assert sl < n_slots, ins.op
+        if ins.op == "SPILL":
+            assert ins.imm < max(al.n_scratch, 1)
+        elif ins.op == "FILL":
+            assert ins.imm < al.n_scratch
+        assert len(ins.ent0) <= isa.LIN_MAX_ENT and len(ins.ent1) <= isa.LIN_MAX_ENT
+        if ins.op in isa.PRODUCT_OPS and ins.has_post():
+            # r' is parked in d (or d2) before the post LIN runs: neither may alias a slot the LIN still reads
+            ent_slots = {t[0] for t in ins.ent0 + ins.ent1}
+            assert ins.d2 not in ent_slots - {ins.r_slot()}
+            if ins.store_r:
+                assert ins.d != ins.d2 and ins.d not in ent_slots - {ins.d}
     arrays = dict(arrays)
     arrays[isa.ARR_OUT] = {}
     interp.run(al.words, pool.values, arrays, al.n_slots, al.n_scratch)
@@ -128,16 +118,17 @@ def test_work_counts_not_above_survey_canonical():
 def test_encode_decode_roundtrip_and_naf():
     w = isa.encode("MUL", d=5, a=255, b=77, c=3, e=9, imm=isa.MUL_B | isa.MUL_ENEG)
     assert isa.decode(w) == ("MUL", 5, 255, 77, 3, 9, isa.MUL_B | isa.MUL_ENEG)
-    assert isa.decode_term(isa.encode_term(13, True, -27, 31)) == (13, True, -27, 31)
+    assert isa.decode_entry(isa.encode_entry(13, 1, 27, True)) == (13, 1, 27, True)
+    assert isa.decode_ext(isa.encode_ext(7, [(3, True), (250, False)], True, 11)) == (7, [(3, True), (250, False)], True, 11)
     assert naf_digits(O.BN_X) == O.get_naf([O.BN_X])[:len(naf_digits(O.BN_X))]
     assert sum(d << i for i, d in enumerate(programs.SIX_U_PLUS_2_NAF)) == 6 * O.BN_X + 2
     assert programs.SIX_U_PLUS_2_NAF == O.SIX_U_PLUS_2_NAF
 
 
-@pytest.mark.parametrize("lin_trees", [False, True])
-def test_optest_program_matches_expectations(lin_trees):
+@pytest.mark.parametrize("mode", [{"enable": False}, {"attach": False}, {}])
+def test_optest_program_matches_expectations(mode):
     """The op-level GPU test's expected values, checked here against the interpreter (incl. edge values),
-    for both lowerings of the linear operations (elementary opcodes / fused LIN trees)."""
+    for all lowerings of the linear operations (elementary opcodes / LIN trees / product epilogues)."""
     import optest_expect as X
 
     rows = X.edge_rows(random.Random(7), n_random=24)
@@ -145,7 +136,7 @@ def test_optest_program_matches_expectations(lin_trees):
         pool = ConstPool()
         b = programs.build_program("optest", pool)
         from plonky2_bn254_pairing_b200.microcode import fuse
-        al = alloc.allocate(fuse.fuse(b.ops, lin_trees=lin_trees), 14)
+        al = alloc.allocate(fuse.fuse(b.ops, **mode), 14)
         arrays = {isa.ARR_F12: r, isa.ARR_OUT: {}}
         interp.run(al.words, pool.values, arrays, al.n_slots, al.n_scratch)
         want = X.expected(r)
@@ -161,7 +152,7 @@ def test_fusion_preserves_results_and_cuts_slot_moves():
     b = programs.build_program("pairing_v0", pool)
     res = {}
     for en in (False, True):
-        al = alloc.allocate(fuse.fuse(b.ops, enable=en, lin_trees=en), 14)
+        al = alloc.allocate(fuse.fuse(b.ops, enable=en), 14)
         arrays = g1g2([PTS[3]])
         arrays[isa.ARR_OUT] = {}
         interp.run(al.words, pool.values, arrays, al.n_slots, al.n_scratch)
@@ -169,3 +160,5 @@ def test_fusion_preserves_results_and_cuts_slot_moves():
     assert res[False][0] == res[True][0] == O.pairing(p, q)
     assert res[True][1]["macs"] == res[False][1]["macs"]
     assert res[True][1]["slot_moves"] < 0.7 * res[False][1]["slot_moves"]
+    lin = sum(res[True][1]["hist"].get(k, 0) for k in ("ADD", "SUB", "DBL", "NEG", "CONJ", "MULXI", "LIN"))
+    assert lin < 2000  # the elementary lowering has ~16 500 stand-alone linear instructions
