@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -25,11 +26,15 @@ struct DevCtx {
     std::vector<u64*> d_prog;  // one device copy per program
     uint4* scratch = nullptr;
     size_t scratch_bytes = 0;
+    u64* state = nullptr;      // phase state of split programs: [2 * n_state][4][stride] u64
+    size_t state_bytes = 0;
+    u32* progress = nullptr;   // per chunk: completed phases
+    size_t progress_count = 0;
     u32* counters = nullptr;   // ring of work counters, one per launch in flight
     unsigned next_counter = 0;
     // staging for the host-pointer API
-    u64* stage[BNP_NARR] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t stage_bytes[BNP_NARR] = {0, 0, 0, 0, 0};
+    u64* stage[BNP_NARR] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t stage_bytes[BNP_NARR] = {0, 0, 0, 0, 0, 0};
 };
 
 std::mutex g_mu;
@@ -63,11 +68,46 @@ DevCtx* find_ctx(int device) {
     return nullptr;
 }
 
+int g_phase_mode = -1;  // -1: automatic, 0: never split, 1: always split when a split variant exists
+
+// cudaMalloc-backed buffer that only grows; the streams are drained before it is replaced
+template <typename P>
+int grow(DevCtx& c, cudaStream_t st, P*& buf, size_t& have, size_t need) {
+    if (need <= have) return BNP_OK;
+    CK(cudaStreamSynchronize(c.stream));
+    if (st != c.stream) CK(cudaStreamSynchronize(st));
+    if (buf) CK(cudaFree(buf));
+    buf = nullptr;
+    have = 0;
+    CK(cudaMalloc(&buf, need));
+    have = need;
+    return BNP_OK;
+}
+
 template <int T>
 int launch_T(DevCtx& c, const BnpProgram& p, int pidx, cudaStream_t st, u64* const arr[BNP_NARR], size_t n,
              size_t stride) {
-    const size_t smem = (size_t)p.n_slots * 64 * T;
     auto kern = bnp_vm_kernel<T>;
+    // phase-split variant "name#K.i" (microcode/phases.py), if the library has one
+    int ph_idx[BNP_MAX_PHASES];
+    int n_ph = 0;
+    for (int K = BNP_MAX_PHASES; K >= 2 && n_ph == 0; K--) {
+        int got = 0;
+        for (int i = 0; i < K; i++) {
+            std::string nm = std::string(p.name) + "#" + std::to_string(K) + "." + std::to_string(i);
+            if (!find_program(nm.c_str(), &ph_idx[i])) break;
+            got++;
+        }
+        if (got == K) n_ph = K;
+    }
+    uint32_t slots = p.n_slots, scratch = p.n_scratch, n_state = 0;
+    for (int i = 0; i < n_ph; i++) {
+        const BnpProgram& q = BNP_PROGRAMS[ph_idx[i]];
+        slots = std::max(slots, q.n_slots);
+        scratch = std::max(scratch, q.n_scratch);
+        n_state = std::max(n_state, q.n_state);
+    }
+    const size_t smem = (size_t)slots * 64 * T;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
@@ -75,22 +115,39 @@ int launch_T(DevCtx& c, const BnpProgram& p, int pidx, cudaStream_t st, u64* con
         g_last_error = "program does not fit in shared memory";
         return BNP_EUNSUPPORTED;
     }
+    const size_t n_chunks = (n + 31) / 32;
+    const size_t resident_warps = (size_t)per_sm * c.sm_count * (T / 32);
+    // Split when the unsplit batch would leave the last round of warp-tasks badly filled.
+    bool split = false;
+    if (n_ph) {
+        const double rounds = (double)n_chunks / (double)resident_warps;
+        const double loss1 = std::ceil(rounds) / rounds - 1.0;
+        const double lossK = std::ceil(rounds * n_ph) / (rounds * n_ph) - 1.0;
+        split = rounds > 1.0 && loss1 > 0.04 && lossK < loss1;
+        if (g_phase_mode == 0) split = false;
+        if (g_phase_mode == 1) split = true;
+    }
     size_t blocks = (n + T - 1) / T;
     blocks = std::min(blocks, (size_t)per_sm * c.sm_count);
     const size_t total = blocks * T;
-    const size_t need = (size_t)std::max<uint32_t>(p.n_scratch, 1) * 64 * total;
-    if (need > c.scratch_bytes) {
-        CK(cudaStreamSynchronize(c.stream));
-        if (st != c.stream) CK(cudaStreamSynchronize(st));
-        if (c.scratch) CK(cudaFree(c.scratch));
-        c.scratch = nullptr;
-        c.scratch_bytes = 0;
-        CK(cudaMalloc(&c.scratch, need));
-        c.scratch_bytes = need;
-    }
+    int rc = grow(c, st, c.scratch, c.scratch_bytes, (size_t)std::max<uint32_t>(scratch, 1) * 64 * total);
+    if (rc) return rc;
     VmArgs a;
-    a.prog = c.d_prog[pidx];
+    for (int i = 0; i < BNP_MAX_PHASES; i++) a.prog[i] = c.d_prog[pidx];
+    a.n_phases = 1;
+    a.progress = nullptr;
     for (int i = 0; i < BNP_NARR; i++) a.arr[i] = arr[i];
+    if (split) {
+        if ((rc = grow(c, st, c.state, c.state_bytes, (size_t)std::max<uint32_t>(n_state, 1) * 64 * stride))) return rc;
+        size_t pbytes = c.progress_count * sizeof(u32);
+        if ((rc = grow(c, st, c.progress, pbytes, n_chunks * sizeof(u32)))) return rc;
+        c.progress_count = pbytes / sizeof(u32);
+        CK(cudaMemsetAsync(c.progress, 0, n_chunks * sizeof(u32), st));
+        for (int i = 0; i < n_ph; i++) a.prog[i] = c.d_prog[ph_idx[i]];
+        a.n_phases = (u32)n_ph;
+        a.progress = c.progress;
+        a.arr[BNP_NARR - 1] = c.state;
+    }
     a.scratch = c.scratch;
     a.n = (u32)n;
     a.stride = (u32)stride;
@@ -116,7 +173,7 @@ int launch(DevCtx& c, const char* prog, void* stream, const u64* g1, const u64* 
     CK(cudaSetDevice(c.dev));
     cudaStream_t st = stream ? (cudaStream_t)stream : c.stream;
     u64* arr[BNP_NARR] = {const_cast<u64*>(g1), const_cast<u64*>(g2), const_cast<u64*>(f12), out,
-                          const_cast<u64*>(aux)};
+                          const_cast<u64*>(aux), nullptr};
     if (stride == 0) stride = n;
     switch (g_threads_per_block) {
         case 32: return launch_T<32>(c, *p, pidx, st, arr, n, stride);
@@ -214,7 +271,7 @@ int run_host(const char* prog, const std::vector<HostIn>& ins, u64* out, size_t 
         if (parts[d].cnt == 0) continue;
         DevCtx& c = g_ctx[d];
         CK(cudaSetDevice(c.dev));
-        const u64* arr[BNP_NARR] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        const u64* arr[BNP_NARR] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
         for (auto& in : ins) {
             int rc = copy_in(c, in.which, in.host, in.K, n, parts[d].off, parts[d].cnt);
             if (rc) return rc;
@@ -286,6 +343,8 @@ void bnp_shutdown(void) {
         for (auto p : c.d_prog)
             if (p) cudaFree(p);
         if (c.scratch) cudaFree(c.scratch);
+        if (c.state) cudaFree(c.state);
+        if (c.progress) cudaFree(c.progress);
         if (c.counters) cudaFree(c.counters);
         for (int i = 0; i < BNP_NARR; i++)
             if (c.stage[i]) cudaFree(c.stage[i]);
@@ -466,8 +525,9 @@ uint64_t bnp_program_macs(const char* program) {
 
 uint64_t bnp_launch_count(void) { return g_launches.load(); }
 
-int bnp_set_launch_config(int threads_per_block, int) {
+int bnp_set_launch_config(int threads_per_block, int phase_mode) {
     std::lock_guard<std::mutex> lk(g_mu);
+    if (phase_mode >= 1 && phase_mode <= 3) g_phase_mode = phase_mode - 2;  // 1 automatic, 2 never split, 3 always split
     if (threads_per_block == 0) return BNP_OK;
     if (threads_per_block != 32 && threads_per_block != 64 && threads_per_block != 128) return BNP_EINVAL;
     g_threads_per_block = threads_per_block;

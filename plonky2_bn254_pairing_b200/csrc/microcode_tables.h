@@ -11,6 +11,7 @@ struct BnpProgram {
     uint64_t macs;          // algorithmic 32x32 MACs per element (64/product + 72/reduction)
     uint32_t products;      // Fp wide products per element
     uint32_t reductions;    // Montgomery reductions per element
+    uint32_t n_state;       // Fq2 values of per-element phase state (phase programs "name#K.i" only)
 };
 
 extern const uint32_t BNP_NCONST;

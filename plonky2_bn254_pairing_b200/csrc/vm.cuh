@@ -14,16 +14,19 @@
 #include "fp2.cuh"
 #include "microcode_ops.h"
 
-#define BNP_NARR 5
+#define BNP_NARR 6
 #define BNP_MAX_CONST 128
+#define BNP_MAX_PHASES 8
 
 struct VmArgs {
-    const u64* prog;        // instruction words (device global memory)
-    u64* arr[BNP_NARR];     // SoA arrays: [K][4][stride] u64 (ids in microcode/isa.py)
+    const u64* prog[BNP_MAX_PHASES];  // instruction words of each phase (device global memory)
+    u64* arr[BNP_NARR];     // SoA arrays: [K][4][stride] u64 (ids in microcode/isa.py); arr[5] = phase state
     uint4* scratch;         // [n_scratch][4][total_threads] uint4
     u32 n;                  // elements to process
     u32 stride;             // elements per limb row of the arrays (>= n)
-    u32* counter;           // work counter (zeroed before launch): warps claim 32-element chunks
+    u32* counter;           // work counter (zeroed before launch): warps claim (phase, 32-element chunk) tasks
+    u32* progress;          // per chunk: number of completed phases (zeroed before launch; unused when n_phases == 1)
+    u32 n_phases;
 };
 
 __device__ __constant__ u32 BNP_CONSTS[BNP_MAX_CONST][16];
@@ -59,7 +62,7 @@ __device__ __forceinline__ void ldg_fp(u32* r, const u64* arr, u32 f, u32 n, u32
     const u64* p = arr + (size_t)f * 4 * n + e;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        u64 v = __ldg(p + (size_t)j * n);
+        u64 v = __ldcg(p + (size_t)j * n);  // L2-coherent: the phase-state array is written by other SMs during the launch
         r[2 * j] = (u32)v;
         r[2 * j + 1] = (u32)(v >> 32);
     }
@@ -253,20 +256,40 @@ __global__ void __launch_bounds__(T) bnp_vm_kernel(VmArgs args) {
     uint4* scr = args.scratch + gtid;
     const u32 n = args.n, stride = args.stride;
 
-    // Persistent warps: each warp claims the next chunk of 32 elements when it finishes one.  A pairing
-    // is ~10 ms of warp time and a 2^16 batch is only ~2 chunks per resident warp, so a static
-    // grid-stride split would leave the last round badly unbalanced.
+    // Persistent warps: each warp claims the next task when it finishes one.  A task is one phase of the
+    // program over one chunk of 32 elements, handed out breadth-first (every chunk's phase 0, then every
+    // chunk's phase 1, ...).  A pairing is ~10 ms of warp time and a 2^16 batch is only 1.73 chunks per
+    // resident warp: unsplit, the second round runs 27 % empty; split in K phases only the last phase does.
+    // Phase p of a chunk waits for phase p-1 of the same chunk, which was claimed n_chunks tasks earlier
+    // by a warp that never waits on anything later - so the wait cannot deadlock and is almost never taken.
     const u32 lane = threadIdx.x & 31u;
+    const u32 n_chunks = (n + 31u) >> 5;
+    const u32 n_tasks = n_chunks * args.n_phases;
     for (;;) {
-        u32 chunk = 0;
-        if (lane == 0) chunk = atomicAdd(args.counter, 1u);
-        chunk = __shfl_sync(0xffffffffu, chunk, 0);
-        const u32 base = chunk * 32u;
-        if (base >= n) break;
-        const u32 e_raw = base + lane;
+        u32 task = 0;
+        if (lane == 0) task = atomicAdd(args.counter, 1u);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= n_tasks) break;
+        const u32 phase = task / n_chunks;
+        const u32 chunk = task - phase * n_chunks;
+        if (phase) {
+            if (lane == 0) {
+                u32 done;
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(done) : "l"(args.progress + chunk) : "memory");
+                    if (done >= phase) break;
+                    __nanosleep(256);
+                }
+            }
+            __syncwarp();
+        }
+        const u32 e_raw = chunk * 32u + lane;
         const bool active = e_raw < n;
         const u32 e = active ? e_raw : n - 1;  // idle lanes shadow the last element and never store
-        const u64* pc = args.prog;
+        const u64* pc = args.prog[0];
+#pragma unroll
+        for (int k = 1; k < BNP_MAX_PHASES; k++)
+            if (phase == (u32)k) pc = args.prog[k];
         u64 ins = __ldg(pc++);
         for (;;) {
             const u32 lo = (u32)ins, hi = (u32)(ins >> 32);
@@ -378,6 +401,12 @@ __global__ void __launch_bounds__(T) bnp_vm_kernel(VmArgs args) {
                     break;
             }
             ins = nxt;
+        }
+        if (args.n_phases > 1u) {  // publish: this chunk's state is complete up to and including `phase`
+            __threadfence();
+            __syncwarp();
+            if (lane == 0)
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(args.progress + chunk), "r"(phase + 1u) : "memory");
         }
     }
 }

@@ -105,8 +105,8 @@ def allocate(ops, n_slots):
         slot_val[s] = v
 
     for i, o in enumerate(ops):
-        if o.op in REMAT:
-            continue  # materialised at first use
+        if o.op in REMAT or o.op == "CUT":
+            continue  # REMAT: materialised at first use; CUT: a phase-boundary marker (phases.py), no code
         all_srcs = o.all_srcs()
         protect = set(all_srcs)
         dsts = o.dsts()

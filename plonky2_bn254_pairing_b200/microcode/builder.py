@@ -155,6 +155,11 @@ class Builder:
     def stg(self, arr, f_lo, f_hi, v):
         self._emit("STG", [v], imm=arr, f_lo=f_lo, f_hi=f_hi, has_dst=False)
 
+    def cut(self):
+        """Candidate phase boundary (microcode/phases.py): the program may be split here into separately
+        scheduled tasks that hand their live values over through the per-element state array."""
+        self._emit("CUT", [], has_dst=False)
+
     # ---- small multiples: a linear pseudo-op that the fusion pass folds into whatever consumes it
     def times(self, a, k):
         assert 1 <= k <= 31
@@ -352,6 +357,7 @@ class Builder:
         started = False
         for z in reversed(naf):
             if started:
+                self.cut()
                 res = self.fq12_cyclo_sqr(res)
             if z != 0:
                 if started:

@@ -67,6 +67,7 @@ ARR_G2 = 1    # [4k Fq][n]   (x.c0, x.c1, y.c0, y.c1)
 ARR_F12 = 2   # [12 Fq][n]   MyFq12 input  (coeffs[0..11])
 ARR_OUT = 3   # [12 Fq][n]   MyFq12 output
 ARR_AUX = 4   # second input array (program specific)
+ARR_STATE = 5 # [2 x state values][n]  values handed from one phase of a split program to the next
 
 MUL_B, MUL_BNEG, MUL_E, MUL_ENEG = 1, 2, 4, 8
 MUL_EXT = 16            # an extension word follows

@@ -151,6 +151,7 @@ def _miller_core(b, n_pairs, track_scale):
     while True:
         if not first:
             # f <- f^2, then one tangent per pair (:152-155, :238-243); R <- 2R (:157, :244-246)
+            b.cut()
             g = b.fq12_sqr(g)
             exp_xi *= 2
             exp_w *= 2
@@ -269,7 +270,9 @@ def _hard_part_ark(b, e):
 
 
 def _final_exp(b, a, variant):
+    b.cut()
     m = _easy_part(b, a)
+    b.cut()
     return _hard_part_ref(b, m) if variant == 0 else _hard_part_ark(b, m)
 
 

@@ -86,6 +86,10 @@ def init(devices=None):
         devices = [int(os.environ.get("LOCAL_RANK", "0"))]
     arr = (_int * len(devices))(*devices)
     check(lib.bnp_init(arr, len(devices)))
+    # tuning knobs for experiments (bnp.h::bnp_set_launch_config); unset = library defaults
+    tpb, phase = int(os.environ.get("BNP_THREADS", "0")), int(os.environ.get("BNP_PHASE_MODE", "0"))
+    if tpb or phase:
+        check(lib.bnp_set_launch_config(tpb, phase))
     _initialised = True
     return lib
 

@@ -162,3 +162,31 @@ def test_fusion_preserves_results_and_cuts_slot_moves():
     assert res[True][1]["slot_moves"] < 0.7 * res[False][1]["slot_moves"]
     lin = sum(res[True][1]["hist"].get(k, 0) for k in ("ADD", "SUB", "DBL", "NEG", "CONJ", "MULXI", "LIN"))
     assert lin < 2000  # the elementary lowering has ~16 500 stand-alone linear instructions
+
+
+@pytest.mark.parametrize("name,k", [("pairing_v0", 4), ("pairing_v1", 3), ("miller", 4), ("final_exp_v0", 2)])
+def test_phase_split_programs_equal_the_monolithic_program(name, k):
+    """microcode/phases.py: K separately allocated phase programs, run in order and handing their live
+    values over through the state array, give the monolithic program's output bit for bit."""
+    from plonky2_bn254_pairing_b200.microcode import fuse, phases
+
+    p, q = PTS[0]
+    pool = ConstPool()
+    fops = fuse.fuse(programs.build_program(name, pool).ops)
+    segs, n_state = phases.split(fops, k)
+    assert len(segs) == k and 0 < n_state <= 40
+    arrays = g1g2([PTS[0]])
+    arrays[isa.ARR_F12] = O.miller_loop_native(q, p)
+    arrays[isa.ARR_OUT] = {}
+    arrays[isa.ARR_STATE] = {}
+    works = []
+    for seg in segs:
+        al = alloc.allocate(seg, 14)
+        interp.run(al.words, pool.values, arrays, al.n_slots, al.n_scratch)
+        works.append(interp.work(al.words)["macs"])
+    got = [arrays[isa.ARR_OUT][i] for i in range(12)]
+    m = O.miller_loop_native(q, p)
+    want = {"pairing_v0": O.final_exp_native(m), "pairing_v1": O.final_exp_ark(m), "miller": m,
+            "final_exp_v0": O.final_exp_native(m)}[name]
+    assert got == want
+    assert max(works) < 1.25 * sum(works) / k  # balanced: the longest phase bounds the partial last round
