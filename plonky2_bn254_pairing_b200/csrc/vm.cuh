@@ -246,8 +246,12 @@ __device__ __forceinline__ void vm_product(const Slots<T>& S, const u64*& pc, u6
     pc = p0 + 2 + nw;
 }
 
+#ifndef BNP_MINB
+#define BNP_MINB 1  // minimum resident blocks per SM the register allocation must allow (blocks of 64 threads)
+#endif
+
 template <int T>
-__global__ void __launch_bounds__(T) bnp_vm_kernel(VmArgs args) {
+__global__ void __launch_bounds__(T, (T == 64) ? BNP_MINB : 1) bnp_vm_kernel(VmArgs args) {
     extern __shared__ uint4 bnp_smem[];
     Slots<T> S;
     S.base = bnp_smem + threadIdx.x;
