@@ -253,7 +253,8 @@ def run_gpu(args):
     native.check(lib.bnp_imad_peak(local, ctypes.byref(peak)))
     peak32 = ctypes.c_double()
     native.check(lib.bnp_imad32_peak(local, ctypes.byref(peak32)))
-    macs = lib.bnp_program_macs(prog.encode())
+    macs = lib.bnp_program_macs(prog.encode())             # algorithmic (Karatsuba Fq2 products), SURVEY 8(d)
+    macs_x = lib.bnp_program_macs_executed(prog.encode())  # what the component-split kernel issues
 
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
@@ -342,6 +343,10 @@ def run_gpu(args):
                 "bound": "imad", "achieved": achieved / 1e9, "peak": peak.value / 1e9, "unit": "GMAC/s",
                 "frac": achieved / peak.value, "traffic": None,
                 "kernel": "bnp_vm_kernel<64>", "kernel_ms_avg": kavg, "macs_per_element": macs,
+                "executed": {"macs_per_element": macs_x, "gmacs": n * macs_x / (kavg * 1e-3) / 1e9,
+                             "pipe_frac": n * macs_x / (kavg * 1e-3) / peak.value,
+                             "note": "the kernel computes an Fq2 product as a two-term dot product per lane "
+                                     "(4 Fp products, not Karatsuba's 3); frac above counts only the algorithmic MACs"},
                 "peak_source": "measured live: bnp_imad_peak (IMAD.WIDE.U32[.X] 4-deep carry chains, 32 MACs/thread/iter); "
                                "MEASURED_PEAKS.json has no integer peak",
                 "imad32_peak_gops": peak32.value / 1e9,

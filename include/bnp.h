@@ -86,6 +86,10 @@ int bnp_fq12_product_dev(int device, void* stream, uint64_t* buf, uint64_t* out,
 /* Algorithmic work of one element of the named program ("pairing_v0", "miller", "final_exp_v0", ...):
  * 32x32->64 multiply-accumulates (64 per Fp product + 72 per Montgomery reduction), 0 if unknown. */
 uint64_t bnp_program_macs(const char* program);
+/* Multiply-accumulates the kernel actually issues for one element: the component-split kernel computes an Fq2
+ * product as a two-term dot product per lane (4 Fp products per Fq2 product instead of Karatsuba's 3), so this
+ * is larger than bnp_program_macs; the ratio of the two is the price paid for doubling the resident warps. */
+uint64_t bnp_program_macs_executed(const char* program);
 /* Kernel launches issued by this library since bnp_init (for bench.py's gpu_launches). */
 uint64_t bnp_launch_count(void);
 /* Dependency-free IMAD.WIDE.U32 throughput microbenchmark on `device`: writes multiply-accumulates

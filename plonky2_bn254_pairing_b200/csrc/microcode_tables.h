@@ -12,6 +12,7 @@ struct BnpProgram {
     uint32_t products;      // Fp wide products per element
     uint32_t reductions;    // Montgomery reductions per element
     uint32_t n_state;       // Fq2 values of per-element phase state (phase programs "name#K.i" only)
+    uint64_t macs_executed; // MACs the component-split kernel issues per element (4-product Fq2 multiplication)
 };
 
 extern const uint32_t BNP_NCONST;

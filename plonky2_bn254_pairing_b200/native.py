@@ -36,6 +36,7 @@ SIGNATURES = {
     "bnp_fq12_mul_dev": (_int, [_int, ctypes.c_void_p, _u64p, _u64p, _u64p, _sz]),
     "bnp_fq12_product_dev": (_int, [_int, ctypes.c_void_p, _u64p, _u64p, _sz]),
     "bnp_program_macs": (ctypes.c_uint64, [ctypes.c_char_p]),
+    "bnp_program_macs_executed": (ctypes.c_uint64, [ctypes.c_char_p]),
     "bnp_launch_count": (ctypes.c_uint64, []),
     "bnp_imad_peak": (_int, [_int, ctypes.POINTER(ctypes.c_double)]),
     "bnp_imad32_peak": (_int, [_int, ctypes.POINTER(ctypes.c_double)]),

@@ -27,7 +27,7 @@ def main():
     d_out = torch.zeros((12, 4, n), dtype=torch.int64, device="cuda")
     stream = torch.cuda.Stream()
     res = {}
-    for T in (32, 64, 128):
+    for T in (64,):
         native.check(lib.bnp_set_launch_config(T, 0))
         for op in os.environ.get("OPS", "mul sqr mulfp add sub dbl neg mulxi lin4 lin4xi muls").split():
             prog = ("opbench_" + op).encode()
@@ -44,7 +44,7 @@ def main():
                 best = ms if best is None else min(best, ms)
             ns_per_op_per_thread = best * 1e6 / 2048 / n  # aggregate: device time per (thread, op)
             # cycles of one SM sub-partition per warp-op: time * clock / (warp-ops per SMSP)
-            warp_ops_per_smsp = (n / 32) * 2048 / (148 * 4)
+            warp_ops_per_smsp = (n / 16) * 2048 / (148 * 4)   # a warp holds 16 pairings (two lanes each)
             cyc = best * 1e-3 * 1.965e9 / warp_ops_per_smsp
             res["%s_T%d" % (op, T)] = {"ms": best, "cycles_per_warp_op_per_smsp": cyc}
             print("T=%3d %-6s %8.2f ms   %7.1f SMSP-cycles per warp-op" % (T, op, best, cyc))
