@@ -98,35 +98,51 @@ __device__ __forceinline__ void chain_acc(u32* x, u32 s, u32 q0, u32 q1, u32 q2,
 }
 
 // ---------------------------------------------------------------------------------------------
-// 256 x 256 -> 512-bit product, 64 IMAD.WIDE + 7 carry captures + 15 merge adds
+// One row of a product or of a Montgomery reduction: two chains with the same multiplier s.
+//   C chain (base D): C[D..D+5] hold data, C[D+6] and C[D+7] are fresh:   C[D..D+7]  = C[D..D+5] + s * (c0, c1, c2, c3)
+//   A chain (base B): A[B..B+7] hold data:                                A[B..B+7] += s * (a0, a1, a2, a3)
+// The A chain starts one limb below the C chain, so its carry out lands exactly on the limb position of
+// C[D+7] and is added there.  C[D+7] = hi(s * c3) + (<= 1) has room for it whenever c3 is a TOP limb below
+// 2^32 - 2: c3 is limb 7 of a value below 4p, or of p.  No carry is ever parked in a limb of its own, so no
+// {carry, 0} register pair has to be built (measured before this form: one SEL + one IMAD.MOV per row,
+// 10 % of all issued instructions were such IMAD.MOVs on the contended multiply pipe).
+// ---------------------------------------------------------------------------------------------
+template <int B, int D>
+__device__ __forceinline__ void mul_row(u32* A, u32* C, u32 s, u32 a0, u32 a1, u32 a2, u32 a3, u32 c0, u32 c1, u32 c2,
+                                        u32 c3) {
+    asm("mad.lo.cc.u32  %0, %16, %21, %0;  madc.hi.cc.u32 %1, %16, %21, %1;\n\t"
+        "madc.lo.cc.u32 %2, %16, %22, %2;  madc.hi.cc.u32 %3, %16, %22, %3;\n\t"
+        "madc.lo.cc.u32 %4, %16, %23, %4;  madc.hi.cc.u32 %5, %16, %23, %5;\n\t"
+        "madc.lo.cc.u32 %6, %16, %24, 0;   madc.hi.u32    %7, %16, %24, 0;\n\t"
+        "mad.lo.cc.u32  %8,  %16, %17, %8;  madc.hi.cc.u32 %9,  %16, %17, %9;\n\t"
+        "madc.lo.cc.u32 %10, %16, %18, %10; madc.hi.cc.u32 %11, %16, %18, %11;\n\t"
+        "madc.lo.cc.u32 %12, %16, %19, %12; madc.hi.cc.u32 %13, %16, %19, %13;\n\t"
+        "madc.lo.cc.u32 %14, %16, %20, %14; madc.hi.cc.u32 %15, %16, %20, %15;\n\t"
+        "addc.u32 %7, %7, 0;"
+        : "+r"(C[D]), "+r"(C[D + 1]), "+r"(C[D + 2]), "+r"(C[D + 3]), "+r"(C[D + 4]), "+r"(C[D + 5]), "=&r"(C[D + 6]),
+          "=&r"(C[D + 7]), "+r"(A[B]), "+r"(A[B + 1]), "+r"(A[B + 2]), "+r"(A[B + 3]), "+r"(A[B + 4]), "+r"(A[B + 5]),
+          "+r"(A[B + 6]), "+r"(A[B + 7])
+        : "r"(s), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(c0), "r"(c1), "r"(c2), "r"(c3));
+}
+
+// ---------------------------------------------------------------------------------------------
+// 256 x 256 -> 512-bit product: 64 IMAD.WIDE + 7 carry adds + 15 merge adds.   Requires b < 2^256 - 2^225.
+// Row i multiplies a[i] into two accumulators of 64-bit columns: E (columns at even limb positions) and
+// O (odd positions; O[k] is limb k + 1).  Even limbs of b land on the accumulator whose columns start at limb i,
+// odd limbs of b on the other one, one limb higher.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fp_mul_wide(u32* r /*16*/, const u32* a /*8*/, const u32* b /*8*/) {
-    u32 E[16], O[16];
-    // row 0
-    chain_fresh<0>(E, a[0], b[0], b[2], b[4], b[6]);
-    chain_fresh<0>(O, a[0], b[1], b[3], b[5], b[7]);
-    // row 1: even limbs of b land on odd positions (O base 0), odd limbs on even positions (E base 2)
-    chain_full<0>(O, a[1], b[0], b[2], b[4], b[6]);
-    chain_top2<2>(E, a[1], b[1], b[3], b[5], b[7]);
-    // row 2
-    chain_full<2>(E, a[2], b[0], b[2], b[4], b[6]);
-    chain_top1<2>(O, a[2], b[1], b[3], b[5], b[7]);
-    // row 3
-    chain_full<2>(O, a[3], b[0], b[2], b[4], b[6]);
-    chain_top1<4>(E, a[3], b[1], b[3], b[5], b[7]);
-    // row 4
-    chain_full<4>(E, a[4], b[0], b[2], b[4], b[6]);
-    chain_top1<4>(O, a[4], b[1], b[3], b[5], b[7]);
-    // row 5
-    chain_full<4>(O, a[5], b[0], b[2], b[4], b[6]);
-    chain_top1<6>(E, a[5], b[1], b[3], b[5], b[7]);
-    // row 6
-    chain_full<6>(E, a[6], b[0], b[2], b[4], b[6]);
-    chain_top1<6>(O, a[6], b[1], b[3], b[5], b[7]);
-    // row 7
-    chain_full<6>(O, a[7], b[0], b[2], b[4], b[6]);
-    chain_top1<8>(E, a[7], b[1], b[3], b[5], b[7]);
-    // merge: r = E + (O << 32)
+    u32 E[16], O[14];
+    chain_fresh<0>(E, a[0], b[0], b[2], b[4], b[6]);                             // limbs 0..7
+    chain_fresh<0>(O, a[0], b[1], b[3], b[5], b[7]);                             // limbs 1..8
+    mul_row<0, 2>(O, E, a[1], b[0], b[2], b[4], b[6], b[1], b[3], b[5], b[7]);   // O: limbs 1..8,  E: limbs 2..9
+    mul_row<2, 2>(E, O, a[2], b[0], b[2], b[4], b[6], b[1], b[3], b[5], b[7]);   // E: limbs 2..9,  O: limbs 3..10
+    mul_row<2, 4>(O, E, a[3], b[0], b[2], b[4], b[6], b[1], b[3], b[5], b[7]);   // O: 3..10,  E: 4..11
+    mul_row<4, 4>(E, O, a[4], b[0], b[2], b[4], b[6], b[1], b[3], b[5], b[7]);   // E: 4..11,  O: 5..12
+    mul_row<4, 6>(O, E, a[5], b[0], b[2], b[4], b[6], b[1], b[3], b[5], b[7]);   // O: 5..12,  E: 6..13
+    mul_row<6, 6>(E, O, a[6], b[0], b[2], b[4], b[6], b[1], b[3], b[5], b[7]);   // E: 6..13,  O: 7..14
+    mul_row<6, 8>(O, E, a[7], b[0], b[2], b[4], b[6], b[1], b[3], b[5], b[7]);   // O: 7..14,  E: 8..15
+    // merge: r = E + (O << 32);  O[0..13] are limbs 1..14
     r[0] = E[0];
     asm("add.cc.u32  %0, %15, %30;\n\t"
         "addc.cc.u32 %1, %16, %31;\n\t"
@@ -142,62 +158,63 @@ __device__ __forceinline__ void fp_mul_wide(u32* r /*16*/, const u32* a /*8*/, c
         "addc.cc.u32 %11, %26, %41;\n\t"
         "addc.cc.u32 %12, %27, %42;\n\t"
         "addc.cc.u32 %13, %28, %43;\n\t"
-        "addc.u32    %14, %29, %44;"
+        "addc.u32    %14, %29, 0;"
         : "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(r[8]),
           "=&r"(r[9]), "=&r"(r[10]), "=&r"(r[11]), "=&r"(r[12]), "=&r"(r[13]), "=&r"(r[14]), "=&r"(r[15])
         : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]),
           "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]), "r"(O[0]), "r"(O[1]),
           "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]), "r"(O[9]), "r"(O[10]),
-          "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
+          "r"(O[11]), "r"(O[12]), "r"(O[13]));
 }
 
 // ---------------------------------------------------------------------------------------------
 // Montgomery reduction rows.  Row i clears limb i of (E + O<<32) by adding m_i * p * 2^(32 i).
 // The limb being cleared lives half in E and half in O; their sum s gives m_i, and the carry of
-// that sum enters the chain that starts one limb higher.
+// that sum enters the chain that starts one limb higher.  Same carry discipline as mul_row: the chain at the
+// cleared limb (even limbs of p) hands its carry to the top limb of the chain one limb higher (odd limbs
+// of p, top product m * P7 < 2^62).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void redc_row0(u32* E, u32* O) {
     u32 m, junk;
-    asm("mul.lo.u32 %17, %0, " BNP_STR(BNP_N0INV) ";\n\t"
-        // O base 0, odd limbs of p, all fresh
-        "mul.lo.u32 %9,  %17, " BNP_STR(BNP_P1) "; mul.hi.u32 %10, %17, " BNP_STR(BNP_P1) ";\n\t"
-        "mul.lo.u32 %11, %17, " BNP_STR(BNP_P3) "; mul.hi.u32 %12, %17, " BNP_STR(BNP_P3) ";\n\t"
-        "mul.lo.u32 %13, %17, " BNP_STR(BNP_P5) "; mul.hi.u32 %14, %17, " BNP_STR(BNP_P5) ";\n\t"
-        "mul.lo.u32 %15, %17, " BNP_STR(BNP_P7) "; mul.hi.u32 %16, %17, " BNP_STR(BNP_P7) ";\n\t"
-        // E base 0, even limbs of p, all data, carry -> E[8]
-        "mad.lo.cc.u32  %18, %17, " BNP_STR(BNP_P0) ", %0; madc.hi.cc.u32 %1, %17, " BNP_STR(BNP_P0) ", %1;\n\t"
-        "madc.lo.cc.u32 %2,  %17, " BNP_STR(BNP_P2) ", %2; madc.hi.cc.u32 %3, %17, " BNP_STR(BNP_P2) ", %3;\n\t"
-        "madc.lo.cc.u32 %4,  %17, " BNP_STR(BNP_P4) ", %4; madc.hi.cc.u32 %5, %17, " BNP_STR(BNP_P4) ", %5;\n\t"
-        "madc.lo.cc.u32 %6,  %17, " BNP_STR(BNP_P6) ", %6; madc.hi.cc.u32 %7, %17, " BNP_STR(BNP_P6) ", %7;\n\t"
-        "addc.u32 %8, 0, 0;"
+    asm("mul.lo.u32 %16, %0, " BNP_STR(BNP_N0INV) ";\n\t"
+        // O base 0 (limbs 1..8), odd limbs of p, all fresh
+        "mul.lo.u32 %8,  %16, " BNP_STR(BNP_P1) "; mul.hi.u32 %9,  %16, " BNP_STR(BNP_P1) ";\n\t"
+        "mul.lo.u32 %10, %16, " BNP_STR(BNP_P3) "; mul.hi.u32 %11, %16, " BNP_STR(BNP_P3) ";\n\t"
+        "mul.lo.u32 %12, %16, " BNP_STR(BNP_P5) "; mul.hi.u32 %13, %16, " BNP_STR(BNP_P5) ";\n\t"
+        "mul.lo.u32 %14, %16, " BNP_STR(BNP_P7) "; mul.hi.u32 %15, %16, " BNP_STR(BNP_P7) ";\n\t"
+        // E base 0 (limbs 0..7), even limbs of p, all data; the low word becomes zero and is dropped; carry -> limb 8 = O[7]
+        "mad.lo.cc.u32  %17, %16, " BNP_STR(BNP_P0) ", %0; madc.hi.cc.u32 %1, %16, " BNP_STR(BNP_P0) ", %1;\n\t"
+        "madc.lo.cc.u32 %2,  %16, " BNP_STR(BNP_P2) ", %2; madc.hi.cc.u32 %3, %16, " BNP_STR(BNP_P2) ", %3;\n\t"
+        "madc.lo.cc.u32 %4,  %16, " BNP_STR(BNP_P4) ", %4; madc.hi.cc.u32 %5, %16, " BNP_STR(BNP_P4) ", %5;\n\t"
+        "madc.lo.cc.u32 %6,  %16, " BNP_STR(BNP_P6) ", %6; madc.hi.cc.u32 %7, %16, " BNP_STR(BNP_P6) ", %7;\n\t"
+        "addc.u32 %15, %15, 0;"
         : "+r"(E[0]), "+r"(E[1]), "+r"(E[2]), "+r"(E[3]), "+r"(E[4]), "+r"(E[5]), "+r"(E[6]), "+r"(E[7]),
-          "=&r"(E[8]), "=&r"(O[0]), "=&r"(O[1]), "=&r"(O[2]), "=&r"(O[3]), "=&r"(O[4]), "=&r"(O[5]), "=&r"(O[6]),
-          "=&r"(O[7]), "=&r"(m), "=&r"(junk));
+          "=&r"(O[0]), "=&r"(O[1]), "=&r"(O[2]), "=&r"(O[3]), "=&r"(O[4]), "=&r"(O[5]), "=&r"(O[6]), "=&r"(O[7]),
+          "=&r"(m), "=&r"(junk));
 }
 
-// A: accumulator whose column starts AT the limb being cleared (entries A[B..B+7] all data, carry -> A[B+8]).
-// C: accumulator whose chain starts one limb higher (entries C[D..D+6] data, C[D+7] fresh); its other
+// A: accumulator whose column starts AT the limb being cleared (A[B..B+7] all data).
+// C: accumulator whose chain starts one limb higher (C[D..D+5] data, C[D+6], C[D+7] fresh); its other
 //    contribution to the cleared limb is the single entry `hi` (already final).
 template <int B, int D>
 __device__ __forceinline__ void redc_row(u32* A, u32* C, u32 hi) {
     u32 m, s, junk;
-    asm("add.cc.u32 %18, %0, %20;\n\t"
-        "mul.lo.u32 %17, %18, " BNP_STR(BNP_N0INV) ";\n\t"
+    asm("add.cc.u32 %17, %0, %19;\n\t"
+        "mul.lo.u32 %16, %17, " BNP_STR(BNP_N0INV) ";\n\t"
         // chain one limb higher: odd limbs of p, carry-in from the add above
-        "madc.lo.cc.u32 %9,  %17, " BNP_STR(BNP_P1) ", %9;  madc.hi.cc.u32 %10, %17, " BNP_STR(BNP_P1) ", %10;\n\t"
-        "madc.lo.cc.u32 %11, %17, " BNP_STR(BNP_P3) ", %11; madc.hi.cc.u32 %12, %17, " BNP_STR(BNP_P3) ", %12;\n\t"
-        "madc.lo.cc.u32 %13, %17, " BNP_STR(BNP_P5) ", %13; madc.hi.cc.u32 %14, %17, " BNP_STR(BNP_P5) ", %14;\n\t"
-        "madc.lo.cc.u32 %15, %17, " BNP_STR(BNP_P7) ", %15; madc.hi.u32    %16, %17, " BNP_STR(BNP_P7) ", 0;\n\t"
-        // chain at the cleared limb: even limbs of p; low word becomes zero and is dropped
-        "mad.lo.cc.u32  %19, %17, " BNP_STR(BNP_P0) ", %18; madc.hi.cc.u32 %1, %17, " BNP_STR(BNP_P0) ", %1;\n\t"
-        "madc.lo.cc.u32 %2,  %17, " BNP_STR(BNP_P2) ", %2;  madc.hi.cc.u32 %3, %17, " BNP_STR(BNP_P2) ", %3;\n\t"
-        "madc.lo.cc.u32 %4,  %17, " BNP_STR(BNP_P4) ", %4;  madc.hi.cc.u32 %5, %17, " BNP_STR(BNP_P4) ", %5;\n\t"
-        "madc.lo.cc.u32 %6,  %17, " BNP_STR(BNP_P6) ", %6;  madc.hi.cc.u32 %7, %17, " BNP_STR(BNP_P6) ", %7;\n\t"
-        "addc.u32 %8, 0, 0;"
+        "madc.lo.cc.u32 %8,  %16, " BNP_STR(BNP_P1) ", %8;  madc.hi.cc.u32 %9,  %16, " BNP_STR(BNP_P1) ", %9;\n\t"
+        "madc.lo.cc.u32 %10, %16, " BNP_STR(BNP_P3) ", %10; madc.hi.cc.u32 %11, %16, " BNP_STR(BNP_P3) ", %11;\n\t"
+        "madc.lo.cc.u32 %12, %16, " BNP_STR(BNP_P5) ", %12; madc.hi.cc.u32 %13, %16, " BNP_STR(BNP_P5) ", %13;\n\t"
+        "madc.lo.cc.u32 %14, %16, " BNP_STR(BNP_P7) ", 0;   madc.hi.u32    %15, %16, " BNP_STR(BNP_P7) ", 0;\n\t"
+        // chain at the cleared limb: even limbs of p; low word becomes zero and is dropped; carry -> C[D+7]
+        "mad.lo.cc.u32  %18, %16, " BNP_STR(BNP_P0) ", %17; madc.hi.cc.u32 %1, %16, " BNP_STR(BNP_P0) ", %1;\n\t"
+        "madc.lo.cc.u32 %2,  %16, " BNP_STR(BNP_P2) ", %2;  madc.hi.cc.u32 %3, %16, " BNP_STR(BNP_P2) ", %3;\n\t"
+        "madc.lo.cc.u32 %4,  %16, " BNP_STR(BNP_P4) ", %4;  madc.hi.cc.u32 %5, %16, " BNP_STR(BNP_P4) ", %5;\n\t"
+        "madc.lo.cc.u32 %6,  %16, " BNP_STR(BNP_P6) ", %6;  madc.hi.cc.u32 %7, %16, " BNP_STR(BNP_P6) ", %7;\n\t"
+        "addc.u32 %15, %15, 0;"
         : "+r"(A[B]), "+r"(A[B + 1]), "+r"(A[B + 2]), "+r"(A[B + 3]), "+r"(A[B + 4]), "+r"(A[B + 5]),
-          "+r"(A[B + 6]), "+r"(A[B + 7]), "=&r"(A[B + 8]), "+r"(C[D]), "+r"(C[D + 1]), "+r"(C[D + 2]),
-          "+r"(C[D + 3]), "+r"(C[D + 4]), "+r"(C[D + 5]), "+r"(C[D + 6]), "=&r"(C[D + 7]), "=&r"(m), "=&r"(s),
-          "=&r"(junk)
+          "+r"(A[B + 6]), "+r"(A[B + 7]), "+r"(C[D]), "+r"(C[D + 1]), "+r"(C[D + 2]), "+r"(C[D + 3]),
+          "+r"(C[D + 4]), "+r"(C[D + 5]), "=&r"(C[D + 6]), "=&r"(C[D + 7]), "=&r"(m), "=&r"(s), "=&r"(junk)
         : "r"(hi));
 }
 
@@ -257,18 +274,18 @@ __device__ __forceinline__ void fp_canon(u32* r, u32 lvl) {
 // 8 IMAD + 64 IMAD.WIDE.
 // fp_redc_lazy: any T < 2^512 - p * 2^256; the result is T / 2^256 + (< p), NOT canonicalised.
 __device__ __forceinline__ void fp_redc_lazy(u32* r /*8*/, const u32* T /*16*/) {
-    u32 E[17], O[16];
+    u32 E[16], O[14];
 #pragma unroll
     for (int i = 0; i < 8; i++) E[i] = T[i];
-    redc_row0(E, O);                 // clears limb 0
-    redc_row<0, 2>(O, E, E[1]);      // row 1: limb 1 = O[0] + E[1];  O chain base 0, E chain base 2
-    redc_row<2, 2>(E, O, O[1]);      // row 2: limb 2 = E[2] + O[1];  E chain base 2, O chain base 2
+    redc_row0(E, O);                 // clears limb 0;  E: limbs 0..7, O: limbs 1..8
+    redc_row<0, 2>(O, E, E[1]);      // row 1: limb 1 = O[0] + E[1];  O chain limbs 1..8, E chain limbs 2..9
+    redc_row<2, 2>(E, O, O[1]);      // row 2: limb 2 = E[2] + O[1];  E chain limbs 2..9, O chain limbs 3..10
     redc_row<2, 4>(O, E, E[3]);      // row 3
     redc_row<4, 4>(E, O, O[3]);      // row 4
     redc_row<4, 6>(O, E, E[5]);      // row 5
-    redc_row<6, 6>(E, O, O[5]);      // row 6
-    redc_row<6, 8>(O, E, E[7]);      // row 7
-    // result limbs k = 0..7: E[8+k] + O[7+k] + T[8+k]
+    redc_row<6, 6>(E, O, O[5]);      // row 6:  E chain limbs 6..13, O chain limbs 7..14
+    redc_row<6, 8>(O, E, E[7]);      // row 7:  O chain limbs 7..14, E chain limbs 8..15
+    // result limbs k = 0..7 (limb 8 + k): E[8+k] + O[7+k] + T[8+k];  O[14] (limb 15) does not exist
     u32 u[8];
     asm("add.cc.u32  %0, %8,  %16;\n\t"
         "addc.cc.u32 %1, %9,  %17;\n\t"
@@ -277,10 +294,10 @@ __device__ __forceinline__ void fp_redc_lazy(u32* r /*8*/, const u32* T /*16*/) 
         "addc.cc.u32 %4, %12, %20;\n\t"
         "addc.cc.u32 %5, %13, %21;\n\t"
         "addc.cc.u32 %6, %14, %22;\n\t"
-        "addc.u32    %7, %15, %23;"
+        "addc.u32    %7, %15, 0;"
         : "=&r"(u[0]), "=&r"(u[1]), "=&r"(u[2]), "=&r"(u[3]), "=&r"(u[4]), "=&r"(u[5]), "=&r"(u[6]), "=&r"(u[7])
         : "r"(E[8]), "r"(E[9]), "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]),
-          "r"(O[7]), "r"(O[8]), "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]));
+          "r"(O[7]), "r"(O[8]), "r"(O[9]), "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]));
     asm("add.cc.u32  %0, %8,  %16;\n\t"
         "addc.cc.u32 %1, %9,  %17;\n\t"
         "addc.cc.u32 %2, %10, %18;\n\t"

@@ -108,7 +108,7 @@ def test_final_exp_is_the_exact_exponent_on_random_input(lib):
 
 
 # ----------------------------------------------------------------------------- batches vs the C oracle (every element, raw limbs)
-@pytest.mark.parametrize("n", [1, 31, 33, 65, 1000])
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 31, 33, 65, 1000])   # a warp holds 16 pairings (two lanes each)
 def test_ragged_batches_bit_exact(lib, cref, n):
     Ps, Qs = point_pool(min(n, 64))
     idx = np.arange(n)
@@ -118,6 +118,26 @@ def test_ragged_batches_bit_exact(lib, cref, n):
     m = api.miller_loop_soa(g1, g2)
     assert np.array_equal(m, cref.miller(g1, g2))
     assert np.array_equal(api.final_exp_soa(m), cref.final_exp(m))
+
+
+@pytest.mark.parametrize("threads", [32, 64, 128, 256, 512])
+@pytest.mark.parametrize("phase_mode", [2, 3])
+def test_every_launch_configuration_bit_exact(lib, cref, threads, phase_mode):
+    """Block size (>= 128 threads: the warps of a block run in lockstep behind a block barrier, idle warps shadow the
+    last chunk) and phase splitting (2: never, 3: always) change the schedule, never the bits."""
+    n = 300
+    Ps, Qs = point_pool(64)
+    idx = np.arange(n)
+    g1 = np.ascontiguousarray(api.pack_soa(api.g1_rows(Ps))[:, :, idx % len(Ps)])
+    g2 = np.ascontiguousarray(api.pack_soa(api.g2_rows(Qs))[:, :, (idx * 5 + 1) % len(Qs)])
+    try:
+        assert lib.bnp_set_launch_config(threads, phase_mode) == 0
+        got = api.pairing_soa(g1, g2)
+        got_m = api.miller_loop_soa(g1, g2)
+    finally:
+        assert lib.bnp_set_launch_config(64, 1) == 0
+    assert np.array_equal(got, cref.pairing(g1, g2))
+    assert np.array_equal(got_m, cref.miller(g1, g2))
 
 
 def test_empty_batch_and_bad_arguments(lib):
