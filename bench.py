@@ -215,6 +215,8 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout; stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = native.init([local])
 

@@ -56,6 +56,17 @@ int bnp_miller_loop_batch(const uint64_t* g1, const uint64_t* g2, uint64_t* out,
 int bnp_multi_miller_loop_batch(const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n, int k);
 /* final_exp_native(a)  (final_exp_native.rs:209). */
 int bnp_final_exp_batch(const uint64_t* in, uint64_t* out, size_t n, int variant);
+/* Witness sourcing for the reference's final-exponentiation CIRCUIT (final_exp_target.rs:65-185): one pass that
+ * returns, per element, the five native MyFq12 values the circuit and its three Fq12ExpU64 starks consume,
+ * out[60][4][n] = { m = easy part (offset BNP_WITNESS_M), m^x, m^(x^2), m^(x^3) (final_exp_target.rs:89-117, the
+ * stark outputs with offset 1), final_exp_native(in) (final_exp_target.rs:240) }, each in MyFq12 coefficient order. */
+#define BNP_WITNESS_M 0
+#define BNP_WITNESS_MX 12
+#define BNP_WITNESS_MX2 24
+#define BNP_WITNESS_MX3 36
+#define BNP_WITNESS_OUT 48
+#define BNP_WITNESS_FQ 60
+int bnp_final_exp_witness_batch(const uint64_t* in, uint64_t* out, size_t n);
 /* pairing(p, q) = final_exp_native(miller_loop_native(&q, &p))  (pairing.rs:20), one fused launch.
  * Output in MyFq12 coefficient order; the Rust wrapper applies MyFq12 -> Fq12. */
 int bnp_pairing_batch(const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n, int variant);
@@ -76,6 +87,7 @@ int bnp_miller_loop_dev(int device, void* stream, const uint64_t* g1, const uint
  * (what bnp_pairing_product reduces and gathers). */
 int bnp_miller_loop_fused_dev(int device, void* stream, const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n);
 int bnp_final_exp_dev(int device, void* stream, const uint64_t* in, uint64_t* out, size_t n, int variant);
+int bnp_final_exp_witness_dev(int device, void* stream, const uint64_t* in, uint64_t* out /* [60][4][n] */, size_t n);
 int bnp_pairing_dev(int device, void* stream, const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n, int k, int variant);
 int bnp_frobenius_dev(int device, void* stream, const uint64_t* in, uint64_t* out, size_t n, size_t power);
 int bnp_fq12_mul_dev(int device, void* stream, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);

@@ -92,6 +92,18 @@ def final_exp_soa(f, variant=VARIANT_REFERENCE):
     return out
 
 
+WITNESS_FIELDS = ("m", "mx", "mx2", "mx3", "out")   # 12 Fq each, in this order (include/bnp.h BNP_WITNESS_*)
+
+
+def final_exp_witness_soa(f):
+    """[12][4][n] -> [60][4][n]: easy part, its three BN_X powers and final_exp_native, one GPU pass."""
+    lib = native.lib()
+    n = f.shape[2]
+    out = np.empty((12 * len(WITNESS_FIELDS), 4, n), dtype=np.uint64)
+    native.check(lib.bnp_final_exp_witness_batch(_ptr(f), _ptr(out), n))
+    return out
+
+
 def pairing_soa(g1, g2, variant=VARIANT_REFERENCE, k=1):
     lib = native.lib()
     n = g1.shape[2]
@@ -151,6 +163,15 @@ def final_exp_native_batch(fs, variant=VARIANT_REFERENCE):
     if not fs:
         return []
     return unpack_soa(final_exp_soa(pack_soa(fs), variant))
+
+
+def final_exp_witness_batch(fs):
+    """The native values the final-exponentiation circuit consumes (final_exp_target.rs:65-185), per input:
+    {"m": easy part, "mx": m^x, "mx2": m^(x^2), "mx3": m^(x^3), "out": final_exp_native(a)}."""
+    if not fs:
+        return []
+    flat = unpack_soa(final_exp_witness_soa(pack_soa(fs)))
+    return [{name: row[12 * i:12 * i + 12] for i, name in enumerate(WITNESS_FIELDS)} for row in flat]
 
 
 def pairing_batch(Ps, Qs, variant=VARIANT_REFERENCE):

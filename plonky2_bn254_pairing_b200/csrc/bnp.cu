@@ -6,6 +6,7 @@
 #include <cmath>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -107,7 +108,9 @@ int launch_T(DevCtx& c, const BnpProgram& p, int pidx, cudaStream_t st, u64* con
         scratch = std::max(scratch, q.n_scratch);
         n_state = std::max(n_state, q.n_state);
     }
-    const size_t smem = (size_t)slots * 32 * T;  // a lane holds one 32-byte Fq component of every slot
+    // a lane holds one 32-byte Fq component of every slot; BNP_SMEM_PAD (experiments only) lowers the occupancy
+    static const size_t pad = std::getenv("BNP_SMEM_PAD") ? (size_t)std::atol(std::getenv("BNP_SMEM_PAD")) : 0;
+    const size_t smem = (size_t)slots * 32 * T + pad;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
@@ -177,6 +180,7 @@ int launch(DevCtx& c, const char* prog, void* stream, const u64* g1, const u64* 
     if (stride == 0) stride = n;
     switch (g_threads_per_block) {
         case 32: return launch_T<32>(c, *p, pidx, st, arr, n, stride);
+        case 96: return launch_T<96>(c, *p, pidx, st, arr, n, stride);
         case 128: return launch_T<128>(c, *p, pidx, st, arr, n, stride);
         case 256: return launch_T<256>(c, *p, pidx, st, arr, n, stride);
         case 512: return launch_T<512>(c, *p, pidx, st, arr, n, stride);
@@ -388,6 +392,10 @@ int bnp_final_exp_batch(const uint64_t* in, uint64_t* out, size_t n, int variant
     return run_host(prog_name("final_exp", 1, variant).c_str(), {{2, in, 12}}, out, 12, n);
 }
 
+int bnp_final_exp_witness_batch(const uint64_t* in, uint64_t* out, size_t n) {
+    return run_host("final_exp_witness", {{2, in, 12}}, out, BNP_WITNESS_FQ, n);
+}
+
 int bnp_pairing_batch(const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n, int variant) {
     if (variant != 0 && variant != 1) return BNP_EINVAL;
     return run_host(prog_name("pairing", 1, variant).c_str(), {{0, g1, 2}, {1, g2, 4}}, out, 12, n);
@@ -488,6 +496,11 @@ int bnp_final_exp_dev(int device, void* stream, const uint64_t* in, uint64_t* ou
     return launch(*c, prog_name("final_exp", 1, variant).c_str(), stream, nullptr, nullptr, in, nullptr, out, n);
 }
 
+int bnp_final_exp_witness_dev(int device, void* stream, const uint64_t* in, uint64_t* out, size_t n) {
+    DEV_PROLOGUE
+    return launch(*c, "final_exp_witness", stream, nullptr, nullptr, in, nullptr, out, n);
+}
+
 int bnp_pairing_dev(int device, void* stream, const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n, int k,
                     int variant) {
     DEV_PROLOGUE
@@ -536,7 +549,8 @@ int bnp_set_launch_config(int threads_per_block, int phase_mode) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (phase_mode >= 1 && phase_mode <= 3) g_phase_mode = phase_mode - 2;  // 1 automatic, 2 never split, 3 always split
     if (threads_per_block == 0) return BNP_OK;
-    if (threads_per_block != 32 && threads_per_block != 64 && threads_per_block != 128 && threads_per_block != 256 &&
+    if (threads_per_block != 32 && threads_per_block != 64 && threads_per_block != 96 && threads_per_block != 128 &&
+        threads_per_block != 256 &&
         threads_per_block != 512)
         return BNP_EINVAL;
     g_threads_per_block = threads_per_block;

@@ -318,7 +318,7 @@ __device__ __forceinline__ void vm_product(const Slots<T>& S, bool comp, u32 op,
 // In lockstep the four warps of a scheduler execute the same lines at nearly the same time, so a line is
 // fetched once per scheduler instead of once per warp.
 template <int T>
-__global__ void __launch_bounds__(T, (BNP_MINB * 64) / T) bnp_vm_kernel(VmArgs args) {
+__global__ void __launch_bounds__(T, (T == 96) ? 6 : (BNP_MINB * 64) / T) bnp_vm_kernel(VmArgs args) {
     constexpr bool LS = T >= BNP_LS_MIN;
     constexpr u32 WPB = T / 32;
     extern __shared__ uint4 bnp_smem[];

@@ -210,18 +210,23 @@ def _easy_part(b, a):
     return b.fq12_mul(f3, f2)
 
 
-def _hard_part_ref(b, m):
-    """final_exp_native.rs:130-169, in the cyclotomic subgroup."""
+def _hard_part_ref(b, m, tap=None):
+    """final_exp_native.rs:130-169, in the cyclotomic subgroup.  `tap(name, value)` is called with the three
+    BN_X powers as soon as each exists (witness program: they are stored and their slots freed early)."""
+    tap = tap or (lambda name, v: None)
     mp = b.fq12_frobenius(m, 1)
     mp2 = b.fq12_frobenius(m, 2)
     mp3 = b.fq12_frobenius(m, 3)
     y0 = b.fq12_mul(mp, b.fq12_mul(mp2, mp3))
     mx = b.fq12_pow_x_cyclo(m)
+    tap("mx", mx)
     mxp = b.fq12_frobenius(mx, 1)
     mx2 = b.fq12_pow_x_cyclo(mx)
+    tap("mx2", mx2)
     mx2p = b.fq12_frobenius(mx2, 1)
     y2 = b.fq12_frobenius(mx2, 2)
     mx3 = b.fq12_pow_x_cyclo(mx2)
+    tap("mx3", mx3)
     mx3p = b.fq12_frobenius(mx3, 1)
     # y1 = conj(m), y3 = conj(mxp), y4 = conj(mx * mx2p), y5 = conj(mx2), y6 = conj(mx3 * mx3p)
     y4c = b.fq12_mul(mx, mx2p)       # conj(y4)
@@ -291,6 +296,26 @@ def prog_miller_fused(b, n_pairs=1):
 def prog_final_exp(b, variant):
     """arr F12 -> OUT: final_exp_native (variant 0) or the ark-compatible exponent (variant 1)."""
     b.st_fq12(isa.ARR_OUT, _final_exp(b, b.ld_fq12(isa.ARR_F12), variant))
+
+
+# Fq offsets of the five MyFq12 values in the witness program's output (include/bnp.h: BNP_WITNESS_*)
+WITNESS_LAYOUT = {"m": 0, "mx": 12, "mx2": 24, "mx3": 36, "out": 48}
+WITNESS_FQ = 60
+
+
+def prog_final_exp_witness(b):
+    """arr F12 -> OUT[60 Fq]: every native value the final-exponentiation CIRCUIT takes from the CPU today
+    (SURVEY 8(f).1): m = easy part (final_exp_target.rs:152-161 recomputes it in-circuit, the value is the input of
+    the first exponentiation stark), m^x, m^(x^2), m^(x^3) = the outputs of the three Fq12ExpU64 starks with
+    offset 1 (final_exp_target.rs:89-117), and final_exp_native(a) itself (the expected public output,
+    final_exp_target.rs:240)."""
+    a = b.ld_fq12(isa.ARR_F12)
+    b.cut()
+    m = _easy_part(b, a)
+    b.st_fq12(isa.ARR_OUT, m, base=WITNESS_LAYOUT["m"])
+    b.cut()
+    out = _hard_part_ref(b, m, tap=lambda name, v: b.st_fq12(isa.ARR_OUT, v, base=WITNESS_LAYOUT[name]))
+    b.st_fq12(isa.ARR_OUT, out, base=WITNESS_LAYOUT["out"])
 
 
 def prog_pairing(b, variant, n_pairs=1):
@@ -401,6 +426,7 @@ PROGRAMS = [
     ("miller_fused", prog_miller_fused, {}),
     ("final_exp_v0", prog_final_exp, {"variant": 0}),
     ("final_exp_v1", prog_final_exp, {"variant": 1}),
+    ("final_exp_witness", prog_final_exp_witness, {}),
     ("pairing_v0", prog_pairing, {"variant": 0}),
     ("pairing_v1", prog_pairing, {"variant": 1}),
     ("fq12_mul", prog_fq12_mul, {}),

@@ -23,6 +23,7 @@ SIGNATURES = {
     "bnp_miller_loop_batch": (_int, [_u64p, _u64p, _u64p, _sz]),
     "bnp_multi_miller_loop_batch": (_int, [_u64p, _u64p, _u64p, _sz, _int]),
     "bnp_final_exp_batch": (_int, [_u64p, _u64p, _sz, _int]),
+    "bnp_final_exp_witness_batch": (_int, [_u64p, _u64p, _sz]),
     "bnp_pairing_batch": (_int, [_u64p, _u64p, _u64p, _sz, _int]),
     "bnp_multi_pairing_batch": (_int, [_u64p, _u64p, _u64p, _sz, _int, _int]),
     "bnp_pairing_product": (_int, [_u64p, _u64p, _u64p, _sz, _int]),
@@ -31,6 +32,7 @@ SIGNATURES = {
     "bnp_miller_loop_dev": (_int, [_int, ctypes.c_void_p, _u64p, _u64p, _u64p, _sz, _int]),
     "bnp_miller_loop_fused_dev": (_int, [_int, ctypes.c_void_p, _u64p, _u64p, _u64p, _sz]),
     "bnp_final_exp_dev": (_int, [_int, ctypes.c_void_p, _u64p, _u64p, _sz, _int]),
+    "bnp_final_exp_witness_dev": (_int, [_int, ctypes.c_void_p, _u64p, _u64p, _sz]),
     "bnp_pairing_dev": (_int, [_int, ctypes.c_void_p, _u64p, _u64p, _u64p, _sz, _int, _int]),
     "bnp_frobenius_dev": (_int, [_int, ctypes.c_void_p, _u64p, _u64p, _sz, _sz]),
     "bnp_fq12_mul_dev": (_int, [_int, ctypes.c_void_p, _u64p, _u64p, _u64p, _sz]),

@@ -13,6 +13,8 @@ extern "C" {
     pub fn bnp_miller_loop_batch(g1: *const u64, g2: *const u64, out: *mut u64, n: usize) -> c_int;
     pub fn bnp_multi_miller_loop_batch(g1: *const u64, g2: *const u64, out: *mut u64, n: usize, k: c_int) -> c_int;
     pub fn bnp_final_exp_batch(input: *const u64, out: *mut u64, n: usize, variant: c_int) -> c_int;
+    /// out: [60][4][n] = easy part, m^x, m^(x^2), m^(x^3), final_exp_native (BNP_WITNESS_* offsets of include/bnp.h)
+    pub fn bnp_final_exp_witness_batch(input: *const u64, out: *mut u64, n: usize) -> c_int;
     pub fn bnp_pairing_batch(g1: *const u64, g2: *const u64, out: *mut u64, n: usize, variant: c_int) -> c_int;
     pub fn bnp_multi_pairing_batch(g1: *const u64, g2: *const u64, out: *mut u64, n: usize, k: c_int, variant: c_int) -> c_int;
     pub fn bnp_pairing_product(g1: *const u64, g2: *const u64, out: *mut u64, n: usize, variant: c_int) -> c_int;

@@ -111,6 +111,28 @@ pub fn final_exp_native_batch(fs: &[MyFq12]) -> Vec<MyFq12> {
     unpack_fq12(&out, n)
 }
 
+/// Native values the final-exponentiation circuit takes as witnesses (final_exp_target.rs:65-185), one GPU pass:
+/// the easy part `m`, the three `Fq12ExpU64` stark outputs `m^x`, `m^(x^2)`, `m^(x^3)` and `final_exp_native(a)`.
+pub struct FinalExpWitness {
+    pub m: MyFq12,
+    pub mx: MyFq12,
+    pub mx2: MyFq12,
+    pub mx3: MyFq12,
+    pub out: MyFq12,
+}
+
+pub fn final_exp_witness_batch(fs: &[MyFq12]) -> Vec<FinalExpWitness> {
+    init();
+    let n = fs.len();
+    let inp = pack_fq12(fs);
+    let mut out = vec![0u64; 4 * 60 * n];
+    check(unsafe { ffi::bnp_final_exp_witness_batch(inp.as_ptr(), out.as_mut_ptr(), n) });
+    let part = |e: usize, base: usize| MyFq12 { coeffs: core::array::from_fn(|k| get(&out, base + k, n, e)) };
+    (0..n)
+        .map(|e| FinalExpWitness { m: part(e, 0), mx: part(e, 12), mx2: part(e, 24), mx3: part(e, 36), out: part(e, 48) })
+        .collect()
+}
+
 pub fn pairing_batch(ps: &[G1Affine], qs: &[G2Affine]) -> Vec<Fq12> {
     assert_eq!(qs.len(), ps.len());
     init();

@@ -107,6 +107,21 @@ def test_final_exp_is_the_exact_exponent_on_random_input(lib):
     assert got1 == [O.fq12_pow(O.fq12_pow(x, exp), O.ARK_LAMBDA) for x in xs]
 
 
+def test_final_exp_witness_values(lib):
+    """The circuit-witness entry point: m, m^x, m^(x^2), m^(x^3), final_exp_native per input."""
+    pts = O.seeded_points(0xB2540009, 3)
+    ins = [O.miller_loop_native(q, p) for p, q in pts]
+    got = api.final_exp_witness_batch(ins)
+    assert api.final_exp_witness_batch([]) == []
+    for a, w in zip(ins, got):
+        m = O.easy_part(a)
+        mx = O.pow_native(m, [O.BN_X])
+        mx2 = O.pow_native(mx, [O.BN_X])
+        mx3 = O.pow_native(mx2, [O.BN_X])
+        assert w == {"m": m, "mx": mx, "mx2": mx2, "mx3": mx3, "out": O.final_exp_native(a)}
+    assert [w["out"] for w in got] == api.final_exp_native_batch(ins)
+
+
 # ----------------------------------------------------------------------------- batches vs the C oracle (every element, raw limbs)
 @pytest.mark.parametrize("n", [1, 15, 16, 17, 31, 33, 65, 1000])   # a warp holds 16 pairings (two lanes each)
 def test_ragged_batches_bit_exact(lib, cref, n):

@@ -31,6 +31,8 @@ def run(name, arrays, n_slots):
     arrays = dict(arrays)
     arrays[isa.ARR_OUT] = {}
     interp.run(al.words, pool.values, arrays, al.n_slots, al.n_scratch)
+    if len(arrays[isa.ARR_OUT]) > 12:
+        return [arrays[isa.ARR_OUT][i] for i in range(len(arrays[isa.ARR_OUT]))], al
     return [arrays[isa.ARR_OUT][i] for i in range(12)], al
 
 
@@ -62,6 +64,23 @@ def test_pairing_and_final_exp(variant, n_slots):
     assert got == want
     got, _ = run("final_exp_v%d" % variant, {isa.ARR_F12: m}, n_slots)
     assert got == want
+
+
+@pytest.mark.parametrize("n_slots", [13, 16])
+def test_final_exp_witness_program(n_slots):
+    """the values final_exp_target.rs takes from the CPU - easy part, its three BN_X powers (the
+    outputs of the Fq12ExpU64 starks, final_exp_target.rs:89-117) and the final result - from one program."""
+    p, q = PTS[2]
+    a = O.miller_loop_native(q, p)
+    got, _ = run("final_exp_witness", {isa.ARR_F12: a}, n_slots)
+    assert len(got) == programs.WITNESS_FQ
+    m = O.easy_part(a)
+    mx = O.pow_native(m, [O.BN_X])
+    mx2 = O.pow_native(mx, [O.BN_X])
+    mx3 = O.pow_native(mx2, [O.BN_X])
+    want = {"m": m, "mx": mx, "mx2": mx2, "mx3": mx3, "out": O.final_exp_native(a)}
+    for name, off in programs.WITNESS_LAYOUT.items():
+        assert got[off:off + 12] == want[name], name
 
 
 def test_final_exp_on_non_miller_input():
