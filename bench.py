@@ -37,6 +37,20 @@ WORKLOADS = {
 }
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read + dram__bytes_write of the sequencer kernel, per launch, from the committed `ncu --set full`
+    capture of this same workload (profiles/ncu_r1_split.txt); None if the summary is missing."""
+    try:
+        tot = 0.0
+        for ln in open(os.path.join(ROOT, "profiles", "ncu_r1_split.txt")):
+            f = ln.split()
+            if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[-1]) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[-2]]
+        return tot or None
+    except (OSError, ValueError, KeyError, IndexError):
+        return None
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -343,7 +357,10 @@ def run_gpu(args):
                        "inputs": "pool of 256 G1 x 256 G2 subgroup points, pair i = (P[i%K], Q[(i/K+7i)%K])"},
             "roofline": {
                 "bound": "imad", "achieved": achieved / 1e9, "peak": peak.value / 1e9, "unit": "GMAC/s",
-                "frac": achieved / peak.value, "traffic": None,
+                "frac": achieved / peak.value,
+                # bytes: one ncu capture at 2^16 pairings (includes the L2-flush write-back and spill traffic that
+                # leaves the L2); not a bound - the algorithmic I/O is 576 B per pairing
+                "traffic": ncu_traffic_bytes() if (args.workload == "pairing" and n == BATCH) else None,
                 "kernel": "bnp_vm_kernel<64>", "kernel_ms_avg": kavg, "macs_per_element": macs,
                 "executed": {"macs_per_element": macs_x, "gmacs": n * macs_x / (kavg * 1e-3) / 1e9,
                              "pipe_frac": n * macs_x / (kavg * 1e-3) / peak.value,
