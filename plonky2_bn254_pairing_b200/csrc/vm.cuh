@@ -173,6 +173,7 @@ __device__ __forceinline__ void vm_lin(const Slots<T>& S, bool comp, u32* out, u
     u32 E[10], O[10];
 #pragma unroll
     for (int i = 0; i < 10; i++) E[i] = O[i] = 0u;
+#ifndef BNP_LIN_SINGLE_COPY
     u32 za[8], ya[8], ta, ua;
     BNP_LIN_FETCH(0u, za, ta);
 #pragma unroll 1
@@ -184,6 +185,15 @@ __device__ __forceinline__ void vm_lin(const Slots<T>& S, bool comp, u32* out, u
         BNP_LIN_ACC(ya, ua);
         if (j + 2u >= n) break;
     }
+#else
+    // one copy of the entry body: 56 instructions smaller, measured 0.5 % slower than the hand-pipelined form above
+#pragma unroll 1
+    for (u32 j = 0; j < n; j++) {
+        u32 za[8], ta;
+        BNP_LIN_FETCH(j, za, ta);
+        BNP_LIN_ACC(za, ta);
+    }
+#endif
     u32 v[9];
     lin_merge(v, E, O);
     fp_reduce_lazy(out, v);
