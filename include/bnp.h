@@ -19,7 +19,8 @@
  *
  * All functions return 0 on success or a negative BNP_E* code; nothing unwinds across the ABI.
  * Host-pointer calls are synchronous.  `*_dev` calls take device pointers on the given device and
- * only enqueue work on `stream` (a cudaStream_t passed as void*; NULL = the library's stream).
+ * only enqueue work on `stream` (a cudaStream_t passed as void*; NULL = the library's own NON-BLOCKING stream, which is not
+ * ordered with the legacy default stream: callers that work on the default stream pass cudaStreamLegacy, (void*)0x1).
  * There is no CPU fallback: without a CUDA device every compute call fails with BNP_ENODEV.
  */
 #ifndef BNP_H

@@ -60,7 +60,13 @@ class DeviceOps:
         self.dev = device_index
 
     def _stream(self):
-        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        # libbnp reads a NULL stream as "the library's own non-blocking stream", which is ordered neither with
+        # torch's default stream nor with the NCCL stream.  torch reports its default stream as handle 0, so name
+        # it explicitly: cudaStreamLegacy (0x1) IS that stream, and everything stays ordered with the tensors
+        # torch made before the call and with the collective that follows (found on 2 GPUs: the partials were
+        # gathered before the tree product had run).
+        h = torch.cuda.current_stream().cuda_stream
+        return ctypes.c_void_p(h if h else 1)
 
     def _out(self, n):
         return torch.empty((12, 4, n), dtype=torch.int64, device="cuda:%d" % self.dev)

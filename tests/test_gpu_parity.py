@@ -209,6 +209,54 @@ def test_global_product_any_count(lib):
     assert api.pairing_product(pairs) == O.final_exp_native(acc)
 
 
+def test_device_ops_on_torch_default_stream(lib):
+    """sharding.DeviceOps enqueues on torch's CURRENT stream.  On the default stream that used to mean handle 0 =
+    the library's own non-blocking stream: unordered with torch's copies (and with NCCL), found on 2 GPUs."""
+    import torch
+
+    from plonky2_bn254_pairing_b200 import sharding
+
+    n = 257
+    Ps, Qs = point_pool(32)
+    idx = np.arange(n)
+    g1 = np.ascontiguousarray(api.pack_soa(api.g1_rows(Ps))[:, :, idx % 32])
+    g2 = np.ascontiguousarray(api.pack_soa(api.g2_rows(Qs))[:, :, (idx * 3 + idx // 32) % 32])
+    want = api.pairing_product_soa(g1, g2)
+    for _ in range(3):  # fresh tensors each time: the host-to-device copies are still in flight when the kernels are enqueued
+        t1 = torch.from_numpy(g1.view(np.int64)).pin_memory().to("cuda:0", non_blocking=True)
+        t2 = torch.from_numpy(g2.view(np.int64)).pin_memory().to("cuda:0", non_blocking=True)
+        out = sharding.pairing_product_distributed(sharding.DeviceOps(0), t1, t2)
+        assert np.array_equal(out.cpu().numpy().view(np.uint64).reshape(12, 4, 1), want)
+
+
+def test_all_devices_in_one_process(lib):
+    """bnp_init on every visible device: host batches are split by index range inside the library and the global
+    product reduces per-device partials over peer copies (skipped on a single-GPU box; tools/gpu_multi_check.py
+    runs the same check plus the torchrun/NCCL variant)."""
+    import torch
+
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs at least two GPUs")
+    try:
+        native.init(list(range(ndev)))
+        n = 500 + ndev
+        Ps, Qs = point_pool(32)
+        idx = np.arange(n)
+        g1 = np.ascontiguousarray(api.pack_soa(api.g1_rows(Ps))[:, :, idx % 32])
+        g2 = np.ascontiguousarray(api.pack_soa(api.g2_rows(Qs))[:, :, (idx * 3 + idx // 32) % 32])
+        got = api.pairing_soa(g1, g2)
+        prod = api.pairing_product_soa(g1, g2)
+    finally:
+        lib.bnp_shutdown()
+        native.init([0])
+    assert np.array_equal(prod, api.pairing_product_soa(g1, g2))
+    acc = np.ascontiguousarray(got[:, :, :1])
+    for i in range(1, 64):
+        acc = api.fq12_mul_soa(acc, np.ascontiguousarray(got[:, :, i:i + 1]))
+    assert np.array_equal(acc, api.pairing_product_soa(np.ascontiguousarray(g1[:, :, :64]), np.ascontiguousarray(g2[:, :, :64])))
+
+
 # ----------------------------------------------------------------------------- BASELINE config 2: 2^16 pairings, every element
 def test_full_size_batch_bit_exact_and_properties(lib, cref):
     n = 1 << 16
