@@ -190,6 +190,26 @@ def test_groth16_shaped_products(lib, cref, k):
     assert np.array_equal(got, acc)
 
 
+@pytest.mark.parametrize("k", [2, 4])
+def test_ark_variant_products(lib, k):
+    """The ark-compatible exponent (variant 1) through the k-way product programs: equal to the product of the
+    single variant-1 pairings, and to the reference value raised to 2x(6x^2+3x+1)."""
+    n = 5
+    Ps, Qs = point_pool(16)
+    rnd = random.Random(100 + k)
+    g1 = np.concatenate([api.pack_soa(api.g1_rows([Ps[rnd.randrange(16)] for _ in range(n)])) for _ in range(k)])
+    g2 = np.concatenate([api.pack_soa(api.g2_rows([Qs[rnd.randrange(16)] for _ in range(n)])) for _ in range(k)])
+    got = api.pairing_soa(g1, g2, variant=api.VARIANT_ARK, k=k)
+    acc = None
+    for j in range(k):
+        single = api.pairing_soa(np.ascontiguousarray(g1[2 * j:2 * j + 2]), np.ascontiguousarray(g2[4 * j:4 * j + 4]),
+                                 variant=api.VARIANT_ARK)
+        acc = single if acc is None else api.fq12_mul_soa(acc, single)
+    assert np.array_equal(got, acc)
+    ref = api.unpack_soa(api.pairing_soa(g1, g2, k=k))
+    assert api.unpack_soa(got) == [O.fq12_pow(x, O.ARK_LAMBDA) for x in ref]
+
+
 def test_frobenius_all_powers(lib, cref):
     rnd = random.Random(12)
     x = api.pack_soa([[rnd.randrange(O.P) for _ in range(12)] for _ in range(40)])
