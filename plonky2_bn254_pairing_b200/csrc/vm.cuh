@@ -129,24 +129,24 @@ __device__ __forceinline__ void fp_kp_minus(u32* r, const u32* a, bool two) {
 // An entry is one pair of 4-deep IMAD.WIDE chains into 64-bit-column accumulators (E: even limb positions,
 // O: odd).  Entries are 16 bits, [slot:8][half:1][neg:1][mult:6], and come in (component 0, component 1)
 // pairs - a lane takes the entry of its own component, so the two lanes of a pairing differ only in the slot
-// address, the negate select and the multiplier.  Two pairs per 64-bit word; the first six pairs arrive in
-// registers, later ones are read from `more`.  The loop is software-pipelined by hand.
+// address, the negate select and the multiplier.  One pair per 32-bit word, fetched through the read-only cache
+// one iteration ahead (the loop is software-pipelined by hand); the negate-select is skipped for pairs in which
+// neither lane negates (a warp-uniform test).
 // ---------------------------------------------------------------------------------------------
-#define BNP_LIN_FETCH(J, Z, TT)                                               \
+#define BNP_LIN_FETCH(J, Z, TT, NG)                                           \
     {                                                                         \
-        u64 w_ = w1;                                                          \
-        if ((J) >= 2u) w_ = w2;                                               \
-        if ((J) >= 4u) w_ = w3;                                               \
-        if ((J) >= 6u) w_ = __ldg(more + ((J) >> 1));                         \
-        const u32 t_ = (u32)(w_ >> (32u * ((J)&1u)));                         \
+        const u32 t_ = __ldg(ents + (J));      /* one (component 0, component 1) pair, same word for every lane */ \
+        NG = (t_ & 0x02000200u) != 0u;         /* warp-uniform: does either lane negate? */                        \
         TT = comp ? (t_ >> 16) : (t_ & 0xffffu);                              \
-        S.load(Z, S.half((TT >> 8) & 1u), TT & 0xffu);                           \
+        S.load(Z, S.half((TT >> 8) & 1u), TT & 0xffu);                        \
     }
-#define BNP_LIN_ACC(Z, TT)                                                    \
+#define BNP_LIN_ACC(Z, TT, NG)                                                \
     {                                                                         \
-        u32 nz_[8];                                                           \
-        fp_p_minus(nz_, Z);                                                   \
-        sel8(Z, (TT & 0x200u) != 0u, nz_, Z);                                 \
+        if (NG) {                                                             \
+            u32 nz_[8];                                                       \
+            fp_p_minus(nz_, Z);                                               \
+            sel8(Z, (TT & 0x200u) != 0u, nz_, Z);                             \
+        }                                                                     \
         chain_acc<0>(E, TT >> 10, Z[0], Z[2], Z[4], Z[6]);                    \
         chain_acc<0>(O, TT >> 10, Z[1], Z[3], Z[5], Z[7]);                    \
     }
@@ -168,21 +168,22 @@ __device__ __forceinline__ void lin_merge(u32* v, const u32* E, const u32* O) {
 }
 
 template <int T>
-__device__ __forceinline__ void vm_lin(const Slots<T>& S, bool comp, u32* out, u32 n, u64 w1, u64 w2, u64 w3,
-                                       const u64* more) {
+__device__ __forceinline__ void vm_lin(const Slots<T>& S, bool comp, u32* out, u32 n, const u64* more) {
+    const u32* ents = (const u32*)more;  // pair j is the j-th 32-bit word of the entry list
     u32 E[10], O[10];
 #pragma unroll
     for (int i = 0; i < 10; i++) E[i] = O[i] = 0u;
 #ifndef BNP_LIN_SINGLE_COPY
     u32 za[8], ya[8], ta, ua;
-    BNP_LIN_FETCH(0u, za, ta);
+    bool na, nu;
+    BNP_LIN_FETCH(0u, za, ta, na);
 #pragma unroll 1
     for (u32 j = 0;; j += 2u) {
-        if (j + 1u < n) BNP_LIN_FETCH(j + 1u, ya, ua);
-        BNP_LIN_ACC(za, ta);
+        if (j + 1u < n) BNP_LIN_FETCH(j + 1u, ya, ua, nu);
+        BNP_LIN_ACC(za, ta, na);
         if (j + 1u >= n) break;
-        if (j + 2u < n) BNP_LIN_FETCH(j + 2u, za, ta);
-        BNP_LIN_ACC(ya, ua);
+        if (j + 2u < n) BNP_LIN_FETCH(j + 2u, za, ta, na);
+        BNP_LIN_ACC(ya, ua, nu);
         if (j + 2u >= n) break;
     }
 #else
@@ -190,8 +191,9 @@ __device__ __forceinline__ void vm_lin(const Slots<T>& S, bool comp, u32* out, u
 #pragma unroll 1
     for (u32 j = 0; j < n; j++) {
         u32 za[8], ta;
-        BNP_LIN_FETCH(j, za, ta);
-        BNP_LIN_ACC(za, ta);
+        bool na;
+        BNP_LIN_FETCH(j, za, ta, na);
+        BNP_LIN_ACC(za, ta, na);
     }
 #endif
     u32 v[9];
@@ -405,10 +407,9 @@ __global__ void __launch_bounds__(T, (T == 96) ? 6 : (BNP_MINB * 64) / T) bnp_vm
             }
             if (op == BNP_OP_LIN) {  // d = LIN(slots), a = number of entry pairs
                 const u32 nw = (a + 1u) >> 1;
-                const u64 w1 = __ldg(pc), w2 = __ldg(pc + 1), w3 = __ldg(pc + 2);
                 const u64 nx = __ldg(pc + nw);
                 u32 o[8];
-                vm_lin<T>(S, comp, o, a, w1, w2, w3, pc);
+                vm_lin<T>(S, comp, o, a, pc);
                 __syncwarp();
                 S.store(d, o);
                 ins = nx;
