@@ -151,6 +151,19 @@ __device__ __forceinline__ void fp_kp_minus(u32* r, const u32* a, bool two) {
         chain_acc<0>(O, TT >> 10, Z[1], Z[3], Z[5], Z[7]);                    \
     }
 
+// first entry of a LIN: the accumulators are written, not accumulated into (no zero-initialisation)
+#define BNP_LIN_ACC_FIRST(Z, TT, NG)                                          \
+    {                                                                         \
+        if (NG) {                                                             \
+            u32 nz_[8];                                                       \
+            fp_p_minus(nz_, Z);                                               \
+            sel8(Z, (TT & 0x200u) != 0u, nz_, Z);                             \
+        }                                                                     \
+        chain_fresh<0>(E, TT >> 10, Z[0], Z[2], Z[4], Z[6]);                  \
+        chain_fresh<0>(O, TT >> 10, Z[1], Z[3], Z[5], Z[7]);                  \
+        E[8] = E[9] = O[8] = O[9] = 0u;                                       \
+    }
+
 // v = E + (O << 32): nine limbs (the total is below 2^264, so limb 9 of either part is zero)
 __device__ __forceinline__ void lin_merge(u32* v, const u32* E, const u32* O) {
     v[0] = E[0];
@@ -171,23 +184,24 @@ template <int T>
 __device__ __forceinline__ void vm_lin(const Slots<T>& S, bool comp, u32* out, u32 n, const u64* more) {
     const u32* ents = (const u32*)more;  // pair j is the j-th 32-bit word of the entry list
     u32 E[10], O[10];
-#pragma unroll
-    for (int i = 0; i < 10; i++) E[i] = O[i] = 0u;
 #ifndef BNP_LIN_SINGLE_COPY
     u32 za[8], ya[8], ta, ua;
     bool na, nu;
     BNP_LIN_FETCH(0u, za, ta, na);
+    if (1u < n) BNP_LIN_FETCH(1u, ya, ua, nu);
+    BNP_LIN_ACC_FIRST(za, ta, na);
 #pragma unroll 1
-    for (u32 j = 0;; j += 2u) {
-        if (j + 1u < n) BNP_LIN_FETCH(j + 1u, ya, ua, nu);
-        BNP_LIN_ACC(za, ta, na);
-        if (j + 1u >= n) break;
-        if (j + 2u < n) BNP_LIN_FETCH(j + 2u, za, ta, na);
+    for (u32 j = 1; j < n; j += 2u) {   // ya holds pair j
+        if (j + 1u < n) BNP_LIN_FETCH(j + 1u, za, ta, na);
         BNP_LIN_ACC(ya, ua, nu);
-        if (j + 2u >= n) break;
+        if (j + 1u >= n) break;
+        if (j + 2u < n) BNP_LIN_FETCH(j + 2u, ya, ua, nu);
+        BNP_LIN_ACC(za, ta, na);
     }
 #else
     // one copy of the entry body: 56 instructions smaller, measured 0.5 % slower than the hand-pipelined form above
+#pragma unroll
+    for (int i = 0; i < 10; i++) E[i] = O[i] = 0u;
 #pragma unroll 1
     for (u32 j = 0; j < n; j++) {
         u32 za[8], ta;
