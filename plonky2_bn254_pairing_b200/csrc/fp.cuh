@@ -97,6 +97,23 @@ __device__ __forceinline__ void chain_acc(u32* x, u32 s, u32 q0, u32 q1, u32 q2,
         : "r"(s), "r"(q0), "r"(q1), "r"(q2), "r"(q3));
 }
 
+// The same accumulation on 64-bit COLUMN variables: x[0..3] += s * (q0..q3), carry added to the low word of x[4].
+// Typing the columns as u64 pins each one to an aligned register pair - inside a loop ptxas otherwise lets the
+// two halves of a loop-carried column drift apart and moves them into a pair and back around every IMAD.WIDE
+// (measured in the LIN loop: 30 moves per 8 multiply-accumulates).
+__device__ __forceinline__ void chain_acc64(u64* x, u32 s, u32 q0, u32 q1, u32 q2, u32 q3) {
+    asm("{ .reg .u32 l0, h0, l1, h1, l2, h2, l3, h3, l4, h4;\n\t"
+        "mov.b64 {l0, h0}, %0; mov.b64 {l1, h1}, %1; mov.b64 {l2, h2}, %2; mov.b64 {l3, h3}, %3; mov.b64 {l4, h4}, %4;\n\t"
+        "mad.lo.cc.u32  l0, %5, %6, l0; madc.hi.cc.u32 h0, %5, %6, h0;\n\t"
+        "madc.lo.cc.u32 l1, %5, %7, l1; madc.hi.cc.u32 h1, %5, %7, h1;\n\t"
+        "madc.lo.cc.u32 l2, %5, %8, l2; madc.hi.cc.u32 h2, %5, %8, h2;\n\t"
+        "madc.lo.cc.u32 l3, %5, %9, l3; madc.hi.cc.u32 h3, %5, %9, h3;\n\t"
+        "addc.u32 l4, l4, 0;\n\t"
+        "mov.b64 %0, {l0, h0}; mov.b64 %1, {l1, h1}; mov.b64 %2, {l2, h2}; mov.b64 %3, {l3, h3}; mov.b64 %4, {l4, h4}; }"
+        : "+l"(x[0]), "+l"(x[1]), "+l"(x[2]), "+l"(x[3]), "+l"(x[4])
+        : "r"(s), "r"(q0), "r"(q1), "r"(q2), "r"(q3));
+}
+
 // ---------------------------------------------------------------------------------------------
 // One row of a product or of a Montgomery reduction: two chains with the same multiplier s.
 //   C chain (base D): C[D..D+5] hold data, C[D+6] and C[D+7] are fresh:   C[D..D+7]  = C[D..D+5] + s * (c0, c1, c2, c3)

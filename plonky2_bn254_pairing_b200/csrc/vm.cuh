@@ -113,14 +113,14 @@ __device__ __forceinline__ void add16(u32* r, const u32* a, const u32* b) {
           "r"(b[11]), "r"(b[12]), "r"(b[13]), "r"(b[14]), "r"(b[15]));
 }
 
-// r = k p - a, k = 1 or 2 (a <= k p)
+// r = k p - a, k = 1 or 2 (a <= k p); `two` is warp-uniform (an instruction flag), the constants are immediates
 __device__ __forceinline__ void fp_kp_minus(u32* r, const u32* a, bool two) {
-    const u32 pp[8] = {(u32)BNP_P0, (u32)BNP_P1, (u32)BNP_P2, (u32)BNP_P3,
-                       (u32)BNP_P4, (u32)BNP_P5, (u32)BNP_P6, (u32)BNP_P7};
-    const u32 p2[8] = {0xb0f9fa8eu, 0x7841182du, 0xd0e3951au, 0x2f02d522u, 0x0302b0bbu, 0x70a08b6du, 0xc2634053u, 0x60c89ce5u};
-    u32 k[8];
-    sel8(k, two, p2, pp);
-    sub8(r, k, a);
+    if (two) {
+        const u32 p2[8] = {0xb0f9fa8eu, 0x7841182du, 0xd0e3951au, 0x2f02d522u, 0x0302b0bbu, 0x70a08b6du, 0xc2634053u, 0x60c89ce5u};
+        sub8(r, p2, a);
+    } else {
+        fp_p_minus(r, a);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -147,8 +147,8 @@ __device__ __forceinline__ void fp_kp_minus(u32* r, const u32* a, bool two) {
             fp_p_minus(nz_, Z);                                               \
             sel8(Z, (TT & 0x200u) != 0u, nz_, Z);                             \
         }                                                                     \
-        chain_acc<0>(E, TT >> 10, Z[0], Z[2], Z[4], Z[6]);                    \
-        chain_acc<0>(O, TT >> 10, Z[1], Z[3], Z[5], Z[7]);                    \
+        chain_acc64(E, TT >> 10, Z[0], Z[2], Z[4], Z[6]);                     \
+        chain_acc64(O, TT >> 10, Z[1], Z[3], Z[5], Z[7]);                     \
     }
 
 // first entry of a LIN: the accumulators are written, not accumulated into (no zero-initialisation)
@@ -159,13 +159,24 @@ __device__ __forceinline__ void fp_kp_minus(u32* r, const u32* a, bool two) {
             fp_p_minus(nz_, Z);                                               \
             sel8(Z, (TT & 0x200u) != 0u, nz_, Z);                             \
         }                                                                     \
-        chain_fresh<0>(E, TT >> 10, Z[0], Z[2], Z[4], Z[6]);                  \
-        chain_fresh<0>(O, TT >> 10, Z[1], Z[3], Z[5], Z[7]);                  \
-        E[8] = E[9] = O[8] = O[9] = 0u;                                       \
+        const u32 m_ = TT >> 10;                                              \
+        _Pragma("unroll") for (int c_ = 0; c_ < 4; c_++) {                    \
+            E[c_] = (u64)m_ * Z[2 * c_];                                      \
+            O[c_] = (u64)m_ * Z[2 * c_ + 1];                                  \
+        }                                                                     \
+        E[4] = O[4] = 0ull;                                                   \
     }
 
 // v = E + (O << 32): nine limbs (the total is below 2^264, so limb 9 of either part is zero)
-__device__ __forceinline__ void lin_merge(u32* v, const u32* E, const u32* O) {
+__device__ __forceinline__ void lin_merge(u32* v, const u64* Ec, const u64* Oc) {
+    u32 E[10], O[10];   // E, O: 64-bit columns at even / odd limb positions
+#pragma unroll
+    for (int c = 0; c < 5; c++) {
+        E[2 * c] = (u32)Ec[c];
+        E[2 * c + 1] = (u32)(Ec[c] >> 32);
+        O[2 * c] = (u32)Oc[c];
+        O[2 * c + 1] = (u32)(Oc[c] >> 32);
+    }
     v[0] = E[0];
     asm("add.cc.u32  %0, %8,  %16;\n\t"
         "addc.cc.u32 %1, %9,  %17;\n\t"
@@ -183,7 +194,7 @@ __device__ __forceinline__ void lin_merge(u32* v, const u32* E, const u32* O) {
 template <int T>
 __device__ __forceinline__ void vm_lin(const Slots<T>& S, bool comp, u32* out, u32 n, const u64* more) {
     const u32* ents = (const u32*)more;  // pair j is the j-th 32-bit word of the entry list
-    u32 E[10], O[10];
+    u64 E[5], O[5];
 #ifndef BNP_LIN_SINGLE_COPY
     u32 za[8], ya[8], ta, ua;
     bool na, nu;
@@ -201,7 +212,7 @@ __device__ __forceinline__ void vm_lin(const Slots<T>& S, bool comp, u32* out, u
 #else
     // one copy of the entry body: 56 instructions smaller, measured 0.5 % slower than the hand-pipelined form above
 #pragma unroll
-    for (int i = 0; i < 10; i++) E[i] = O[i] = 0u;
+    for (int i = 0; i < 5; i++) E[i] = O[i] = 0ull;
 #pragma unroll 1
     for (u32 j = 0; j < n; j++) {
         u32 za[8], ta;
