@@ -467,8 +467,9 @@ __global__ void __launch_bounds__(T, (T == 96) ? 6 : (BNP_MINB * 64) / T) bnp_vm
                 case BNP_OP_FILL: {
                     uint4* p = S.own + d * (2 * T);
                     const uint4* q = scr + (size_t)imm * 2 * total;
-                    p[0] = q[0];
-                    p[T] = q[total];
+                    // read-once data: bypass L1 (what little L1 the slots leave holds the instruction words)
+                    p[0] = __ldcg(q);
+                    p[T] = __ldcg(q + total);
                     break;
                 }
                 case BNP_OP_INV: {  // once or twice per program: both lanes run the whole Fq2 inversion
