@@ -35,13 +35,14 @@ __device__ __constant__ u32 BNP_P[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0
 // column chains: x[B .. B+7] (+)= s * (q0, q1, q2, q3), four 64-bit columns with carry between them
 // ---------------------------------------------------------------------------------------------
 
-// all eight limbs fresh: four independent wide products
+// all eight limbs fresh: four independent wide products (mul.wide, so that each is ONE IMAD.WIDE - written as
+// mul.lo / mul.hi pairs ptxas fuses only some of them)
 template <int B>
 __device__ __forceinline__ void chain_fresh(u32* x, u32 s, u32 q0, u32 q1, u32 q2, u32 q3) {
-    asm("mul.lo.u32 %0, %8, %9;  mul.hi.u32 %1, %8, %9;\n\t"
-        "mul.lo.u32 %2, %8, %10; mul.hi.u32 %3, %8, %10;\n\t"
-        "mul.lo.u32 %4, %8, %11; mul.hi.u32 %5, %8, %11;\n\t"
-        "mul.lo.u32 %6, %8, %12; mul.hi.u32 %7, %8, %12;"
+    asm("{ .reg .u64 t0, t1, t2, t3;\n\t"
+        "mul.wide.u32 t0, %8, %9;  mul.wide.u32 t1, %8, %10;\n\t"
+        "mul.wide.u32 t2, %8, %11; mul.wide.u32 t3, %8, %12;\n\t"
+        "mov.b64 {%0, %1}, t0; mov.b64 {%2, %3}, t1; mov.b64 {%4, %5}, t2; mov.b64 {%6, %7}, t3; }"
         : "=&r"(x[B]), "=&r"(x[B + 1]), "=&r"(x[B + 2]), "=&r"(x[B + 3]), "=&r"(x[B + 4]), "=&r"(x[B + 5]),
           "=&r"(x[B + 6]), "=&r"(x[B + 7])
         : "r"(s), "r"(q0), "r"(q1), "r"(q2), "r"(q3));
