@@ -194,18 +194,18 @@ __device__ __forceinline__ void fp_mul_wide(u32* r /*16*/, const u32* a /*8*/, c
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void redc_row0(u32* E, u32* O) {
     u32 m, junk;
-    asm("mul.lo.u32 %16, %0, " BNP_STR(BNP_N0INV) ";\n\t"
+    asm("{ .reg .u64 t0, t1, t2, t3;\n\t"
+        "mul.lo.u32 %16, %0, " BNP_STR(BNP_N0INV) ";\n\t"
         // O base 0 (limbs 1..8), odd limbs of p, all fresh
-        "mul.lo.u32 %8,  %16, " BNP_STR(BNP_P1) "; mul.hi.u32 %9,  %16, " BNP_STR(BNP_P1) ";\n\t"
-        "mul.lo.u32 %10, %16, " BNP_STR(BNP_P3) "; mul.hi.u32 %11, %16, " BNP_STR(BNP_P3) ";\n\t"
-        "mul.lo.u32 %12, %16, " BNP_STR(BNP_P5) "; mul.hi.u32 %13, %16, " BNP_STR(BNP_P5) ";\n\t"
-        "mul.lo.u32 %14, %16, " BNP_STR(BNP_P7) "; mul.hi.u32 %15, %16, " BNP_STR(BNP_P7) ";\n\t"
+        "mul.wide.u32 t0, %16, " BNP_STR(BNP_P1) "; mul.wide.u32 t1, %16, " BNP_STR(BNP_P3) ";\n\t"
+        "mul.wide.u32 t2, %16, " BNP_STR(BNP_P5) "; mul.wide.u32 t3, %16, " BNP_STR(BNP_P7) ";\n\t"
+        "mov.b64 {%8, %9}, t0; mov.b64 {%10, %11}, t1; mov.b64 {%12, %13}, t2; mov.b64 {%14, %15}, t3;\n\t"
         // E base 0 (limbs 0..7), even limbs of p, all data; the low word becomes zero and is dropped; carry -> limb 8 = O[7]
         "mad.lo.cc.u32  %17, %16, " BNP_STR(BNP_P0) ", %0; madc.hi.cc.u32 %1, %16, " BNP_STR(BNP_P0) ", %1;\n\t"
         "madc.lo.cc.u32 %2,  %16, " BNP_STR(BNP_P2) ", %2; madc.hi.cc.u32 %3, %16, " BNP_STR(BNP_P2) ", %3;\n\t"
         "madc.lo.cc.u32 %4,  %16, " BNP_STR(BNP_P4) ", %4; madc.hi.cc.u32 %5, %16, " BNP_STR(BNP_P4) ", %5;\n\t"
         "madc.lo.cc.u32 %6,  %16, " BNP_STR(BNP_P6) ", %6; madc.hi.cc.u32 %7, %16, " BNP_STR(BNP_P6) ", %7;\n\t"
-        "addc.u32 %15, %15, 0;"
+        "addc.u32 %15, %15, 0; }"
         : "+r"(E[0]), "+r"(E[1]), "+r"(E[2]), "+r"(E[3]), "+r"(E[4]), "+r"(E[5]), "+r"(E[6]), "+r"(E[7]),
           "=&r"(O[0]), "=&r"(O[1]), "=&r"(O[2]), "=&r"(O[3]), "=&r"(O[4]), "=&r"(O[5]), "=&r"(O[6]), "=&r"(O[7]),
           "=&r"(m), "=&r"(junk));
