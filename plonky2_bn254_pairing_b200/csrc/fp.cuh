@@ -186,6 +186,100 @@ __device__ __forceinline__ void fp_mul_wide(u32* r /*16*/, const u32* a /*8*/, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// Two-term dot product  r = a * b + a2 * b2  (512 bits) in ONE pair of column accumulators: row i multiplies a[i]
+// into the columns and then a2[i] into the SAME columns, so there is one merge instead of two merges and a 512-bit
+// add.  Requires b, b2 <= 2p: their top limbs are below 2^31, so the top column of the odd chain,
+// a[i] b[7] + a2[i] b2[7] + carries, still fits 64 bits and keeps room for the carries of the even chain.
+// ---------------------------------------------------------------------------------------------
+template <int B, int D>
+__device__ __forceinline__ void mul2_row(u32* A, u32* C, u32 s, u32 s2, const u32* b, const u32* b2) {
+    asm(// C chain, first term: top two limbs fresh
+        "mad.lo.cc.u32  %0, %16, %19, %0;  madc.hi.cc.u32 %1, %16, %19, %1;\n\t"
+        "madc.lo.cc.u32 %2, %16, %21, %2;  madc.hi.cc.u32 %3, %16, %21, %3;\n\t"
+        "madc.lo.cc.u32 %4, %16, %23, %4;  madc.hi.cc.u32 %5, %16, %23, %5;\n\t"
+        "madc.lo.cc.u32 %6, %16, %25, 0;   madc.hi.u32    %7, %16, %25, 0;\n\t"
+        // C chain, second term: all eight limbs hold data, no carry out (see above)
+        "mad.lo.cc.u32  %0, %17, %27, %0;  madc.hi.cc.u32 %1, %17, %27, %1;\n\t"
+        "madc.lo.cc.u32 %2, %17, %29, %2;  madc.hi.cc.u32 %3, %17, %29, %3;\n\t"
+        "madc.lo.cc.u32 %4, %17, %31, %4;  madc.hi.cc.u32 %5, %17, %31, %5;\n\t"
+        "madc.lo.cc.u32 %6, %17, %33, %6;  madc.hi.u32    %7, %17, %33, %7;\n\t"
+        // A chain, first term; carry -> C top limb
+        "mad.lo.cc.u32  %8,  %16, %18, %8;  madc.hi.cc.u32 %9,  %16, %18, %9;\n\t"
+        "madc.lo.cc.u32 %10, %16, %20, %10; madc.hi.cc.u32 %11, %16, %20, %11;\n\t"
+        "madc.lo.cc.u32 %12, %16, %22, %12; madc.hi.cc.u32 %13, %16, %22, %13;\n\t"
+        "madc.lo.cc.u32 %14, %16, %24, %14; madc.hi.cc.u32 %15, %16, %24, %15;\n\t"
+        "addc.u32 %7, %7, 0;\n\t"
+        // A chain, second term; carry -> C top limb
+        "mad.lo.cc.u32  %8,  %17, %26, %8;  madc.hi.cc.u32 %9,  %17, %26, %9;\n\t"
+        "madc.lo.cc.u32 %10, %17, %28, %10; madc.hi.cc.u32 %11, %17, %28, %11;\n\t"
+        "madc.lo.cc.u32 %12, %17, %30, %12; madc.hi.cc.u32 %13, %17, %30, %13;\n\t"
+        "madc.lo.cc.u32 %14, %17, %32, %14; madc.hi.cc.u32 %15, %17, %32, %15;\n\t"
+        "addc.u32 %7, %7, 0;"
+        : "+r"(C[D]), "+r"(C[D + 1]), "+r"(C[D + 2]), "+r"(C[D + 3]), "+r"(C[D + 4]), "+r"(C[D + 5]), "=&r"(C[D + 6]),
+          "=&r"(C[D + 7]), "+r"(A[B]), "+r"(A[B + 1]), "+r"(A[B + 2]), "+r"(A[B + 3]), "+r"(A[B + 4]), "+r"(A[B + 5]),
+          "+r"(A[B + 6]), "+r"(A[B + 7])
+        : "r"(s), "r"(s2), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]),
+          "r"(b2[0]), "r"(b2[1]), "r"(b2[2]), "r"(b2[3]), "r"(b2[4]), "r"(b2[5]), "r"(b2[6]), "r"(b2[7]));
+}
+
+// row 0: the first term writes the columns, the second accumulates (E: limbs 0..7, carry -> O[7]; O: limbs 1..8)
+__device__ __forceinline__ void mul2_row0(u32* E, u32* O, u32 s, u32 s2, const u32* b, const u32* b2) {
+    chain_fresh<0>(E, s, b[0], b[2], b[4], b[6]);
+    chain_fresh<0>(O, s, b[1], b[3], b[5], b[7]);
+    asm("mad.lo.cc.u32  %0, %16, %18, %0;  madc.hi.cc.u32 %1, %16, %18, %1;\n\t"
+        "madc.lo.cc.u32 %2, %16, %20, %2;  madc.hi.cc.u32 %3, %16, %20, %3;\n\t"
+        "madc.lo.cc.u32 %4, %16, %22, %4;  madc.hi.cc.u32 %5, %16, %22, %5;\n\t"
+        "madc.lo.cc.u32 %6, %16, %24, %6;  madc.hi.u32    %7, %16, %24, %7;\n\t"
+        "mad.lo.cc.u32  %8,  %16, %17, %8;  madc.hi.cc.u32 %9,  %16, %17, %9;\n\t"
+        "madc.lo.cc.u32 %10, %16, %19, %10; madc.hi.cc.u32 %11, %16, %19, %11;\n\t"
+        "madc.lo.cc.u32 %12, %16, %21, %12; madc.hi.cc.u32 %13, %16, %21, %13;\n\t"
+        "madc.lo.cc.u32 %14, %16, %23, %14; madc.hi.cc.u32 %15, %16, %23, %15;\n\t"
+        "addc.u32 %7, %7, 0;"
+        : "+r"(O[0]), "+r"(O[1]), "+r"(O[2]), "+r"(O[3]), "+r"(O[4]), "+r"(O[5]), "+r"(O[6]), "+r"(O[7]), "+r"(E[0]),
+          "+r"(E[1]), "+r"(E[2]), "+r"(E[3]), "+r"(E[4]), "+r"(E[5]), "+r"(E[6]), "+r"(E[7])
+        : "r"(s2), "r"(b2[0]), "r"(b2[1]), "r"(b2[2]), "r"(b2[3]), "r"(b2[4]), "r"(b2[5]), "r"(b2[6]), "r"(b2[7]));
+}
+
+__device__ __forceinline__ void wide_merge(u32* r /*16*/, const u32* E /*16*/, const u32* O /*14*/) {
+    // r = E + (O << 32);  O[0..13] are limbs 1..14
+    r[0] = E[0];
+    asm("add.cc.u32  %0, %15, %30;\n\t"
+        "addc.cc.u32 %1, %16, %31;\n\t"
+        "addc.cc.u32 %2, %17, %32;\n\t"
+        "addc.cc.u32 %3, %18, %33;\n\t"
+        "addc.cc.u32 %4, %19, %34;\n\t"
+        "addc.cc.u32 %5, %20, %35;\n\t"
+        "addc.cc.u32 %6, %21, %36;\n\t"
+        "addc.cc.u32 %7, %22, %37;\n\t"
+        "addc.cc.u32 %8, %23, %38;\n\t"
+        "addc.cc.u32 %9, %24, %39;\n\t"
+        "addc.cc.u32 %10, %25, %40;\n\t"
+        "addc.cc.u32 %11, %26, %41;\n\t"
+        "addc.cc.u32 %12, %27, %42;\n\t"
+        "addc.cc.u32 %13, %28, %43;\n\t"
+        "addc.u32    %14, %29, 0;"
+        : "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(r[8]),
+          "=&r"(r[9]), "=&r"(r[10]), "=&r"(r[11]), "=&r"(r[12]), "=&r"(r[13]), "=&r"(r[14]), "=&r"(r[15])
+        : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(E[9]),
+          "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]), "r"(O[0]), "r"(O[1]),
+          "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]), "r"(O[8]), "r"(O[9]), "r"(O[10]),
+          "r"(O[11]), "r"(O[12]), "r"(O[13]));
+}
+
+__device__ __forceinline__ void fp_mul2_wide(u32* r /*16*/, const u32* a, const u32* b, const u32* a2, const u32* b2) {
+    u32 E[16], O[14];
+    mul2_row0(E, O, a[0], a2[0], b, b2);
+    mul2_row<0, 2>(O, E, a[1], a2[1], b, b2);
+    mul2_row<2, 2>(E, O, a[2], a2[2], b, b2);
+    mul2_row<2, 4>(O, E, a[3], a2[3], b, b2);
+    mul2_row<4, 4>(E, O, a[4], a2[4], b, b2);
+    mul2_row<4, 6>(O, E, a[5], a2[5], b, b2);
+    mul2_row<6, 6>(E, O, a[6], a2[6], b, b2);
+    mul2_row<6, 8>(O, E, a[7], a2[7], b, b2);
+    wide_merge(r, E, O);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Montgomery reduction rows.  Row i clears limb i of (E + O<<32) by adding m_i * p * 2^(32 i).
 // The limb being cleared lives half in E and half in O; their sum s gives m_i, and the carry of
 // that sum enters the chain that starts one limb higher.  Same carry discipline as mul_row: the chain at the

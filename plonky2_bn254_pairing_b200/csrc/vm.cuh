@@ -291,12 +291,10 @@ __device__ __forceinline__ void vm_product(const Slots<T>& S, bool comp, u32 op,
         S.load(v1, S.half(imm & BNP_MULFP_HALF), b);
     }
     u32 TT[16];
-    fp_mul_wide(TT, u1, v1);
-    if (op == BNP_OP_MUL) {
-        u32 Pb[16];
-        fp_mul_wide(Pb, u2, v2);
-        add16(TT, TT, Pb);
-    }
+    if (op == BNP_OP_MUL)
+        fp_mul2_wide(TT, u1, v1, u2, v2);  // both terms in one pair of column accumulators (v1, v2 <= 2p)
+    else
+        fp_mul_wide(TT, u1, v1);
     u32 np = 0, d2 = 0;  // np: entry pairs of the post LIN
     bool store_r = true;
     if (imm & BNP_MUL_EXT) {
