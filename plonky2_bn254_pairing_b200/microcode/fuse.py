@@ -2,9 +2,8 @@
 (MUL / SQR / MULFP with pre-additions, hi terms and a post LIN stage), INV, loads/stores and the few linear
 instructions that could not be attached to a product.
 
-Why (measured on B200, profiles/): a stand-alone linear opcode costs ~250-450 sub-partition cycles, nearly all
-of it dispatch and shared-memory traffic (three 64-byte slot moves per thread at 128 B/clk/SM) for ~100 cycles
-of arithmetic, and the tower formulas contain ~2.6 of them per multiplication.  Almost every linear value in a
+Why (measured on B200, profiles/): a stand-alone linear opcode costs ~140-240 sub-partition cycles per warp-op,
+nearly all of it dispatch, slot traffic and the serial carry chain of the modular step, and the tower formulas contain ~2.6 of them per multiplication.  Almost every linear value in a
 pairing is `product +- older values` (Karatsuba recombination, v-multiplication, 3x-2y in the cyclotomic
 squaring, the Fq12-level even/odd halves), so it is computed in the epilogue of the product that completes it:
 
