@@ -229,9 +229,19 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout; stdout carries ONE JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints a "NCCL version ..." banner on STDOUT when the first communicator is created; stdout carries
+        # ONE JSON line, so the file descriptor points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize(local)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     lib = native.init([local])
 
     prog, k, label = WORKLOADS[args.workload]
