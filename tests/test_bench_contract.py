@@ -32,3 +32,16 @@ def test_ours_arm_fails_loudly_without_a_gpu():
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode != 0
     assert not any(ln.startswith("{") and '"value"' in ln for ln in out.stdout.splitlines())
+
+
+def test_reference_arm_under_torchrun_prints_on_rank0_only():
+    """N > 1: the driver launches the reference arm with torchrun too; rank 0 alone runs and prints."""
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29557", os.path.join(ROOT, "bench.py"),
+                          "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2
