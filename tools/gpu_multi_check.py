@@ -70,6 +70,34 @@ def distributed():
     dist.barrier()
     if rank == 0:
         print("torchrun, %d ranks: NCCL-gathered global product bit-exact on every rank" % world)
+    # timing of the one-product shape of BASELINE config 4: 2^20 pairs in total, fused Miller loops, per-GPU tree
+    # product, 384-byte all-gather, one final exponentiation (device-resident inputs, CUDA events, max over ranks)
+    if os.environ.get("BNP_TIME_PRODUCT", "1") != "0":
+        from plonky2_bn254_pairing_b200 import workload as wl
+
+        n_loc = (1 << 20) // world
+        h1, h2, _ = wl.pairing_inputs(n_loc, k=1, offset=rank * n_loc)
+        b1 = torch.from_numpy(h1.view(np.int64)).to(dev)
+        b2 = torch.from_numpy(h2.view(np.int64)).to(dev)
+        ops = sharding.DeviceOps(local)
+        for _ in range(2):
+            sharding.pairing_product_distributed(ops, b1, b2)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record()
+        for _ in range(reps):
+            res = sharding.pairing_product_distributed(ops, b1, b2)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            ms = float(t.item())
+            print("global product of 2^20 pairs on %d GPU(s): %.2f ms per product = %.2f M pairs/s (Miller fused + tree product + "
+                  "384 B all-gather + one final exponentiation)" % (world, ms, (1 << 20) / ms / 1e3))
+        del res
     dist.destroy_process_group()
 
 
