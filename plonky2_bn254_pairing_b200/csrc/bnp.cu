@@ -41,7 +41,7 @@ struct DevCtx {
 std::mutex g_mu;
 std::vector<DevCtx> g_ctx;
 std::atomic<uint64_t> g_launches{0};
-int g_threads_per_block = 64;  // measured best (profiles/threads_sweep_r1.txt); 128+ run in lockstep (vm.cuh)
+int g_threads_per_block = 64;  // 4 blocks of 64 threads per SM: 8 resident warps, the shared-memory limit of 14 slots
 thread_local std::string g_last_error;
 
 int cuda_fail(cudaError_t e, const char* what) {
@@ -108,9 +108,9 @@ int launch_T(DevCtx& c, const BnpProgram& p, int pidx, cudaStream_t st, u64* con
         scratch = std::max(scratch, q.n_scratch);
         n_state = std::max(n_state, q.n_state);
     }
-    // a lane holds one 32-byte Fq component of every slot; BNP_SMEM_PAD (experiments only) lowers the occupancy
+    // a thread holds the 64-byte Fq2 value of every slot; BNP_SMEM_PAD (experiments only) lowers the occupancy
     static const size_t pad = std::getenv("BNP_SMEM_PAD") ? (size_t)std::atol(std::getenv("BNP_SMEM_PAD")) : 0;
-    const size_t smem = (size_t)slots * 32 * T + pad;
+    const size_t smem = (size_t)slots * 64 * T + pad;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
@@ -118,7 +118,7 @@ int launch_T(DevCtx& c, const BnpProgram& p, int pidx, cudaStream_t st, u64* con
         g_last_error = "program does not fit in shared memory";
         return BNP_EUNSUPPORTED;
     }
-    const size_t n_chunks = (n + BNP_CHUNK - 1) / BNP_CHUNK;  // a warp works on 16 pairings, two lanes each
+    const size_t n_chunks = (n + BNP_CHUNK - 1) / BNP_CHUNK;  // a warp works on 32 pairings, one per lane
     const size_t resident_warps = (size_t)per_sm * c.sm_count * (T / 32);
     // Split when the unsplit batch would leave the last round of warp-tasks badly filled.
     bool split = false;
@@ -130,10 +130,10 @@ int launch_T(DevCtx& c, const BnpProgram& p, int pidx, cudaStream_t st, u64* con
         if (g_phase_mode == 0) split = false;
         if (g_phase_mode == 1) split = true;
     }
-    size_t blocks = (2 * n + T - 1) / T;
+    size_t blocks = (n + T - 1) / T;
     blocks = std::min(blocks, (size_t)per_sm * c.sm_count);
     const size_t total = blocks * T;
-    int rc = grow(c, st, c.scratch, c.scratch_bytes, (size_t)std::max<uint32_t>(scratch, 1) * 32 * total);
+    int rc = grow(c, st, c.scratch, c.scratch_bytes, (size_t)std::max<uint32_t>(scratch, 1) * 64 * total);
     if (rc) return rc;
     VmArgs a;
     for (int i = 0; i < BNP_MAX_PHASES; i++) a.prog[i] = c.d_prog[pidx];
@@ -180,10 +180,8 @@ int launch(DevCtx& c, const char* prog, void* stream, const u64* g1, const u64* 
     if (stride == 0) stride = n;
     switch (g_threads_per_block) {
         case 32: return launch_T<32>(c, *p, pidx, st, arr, n, stride);
-        case 96: return launch_T<96>(c, *p, pidx, st, arr, n, stride);
         case 128: return launch_T<128>(c, *p, pidx, st, arr, n, stride);
         case 256: return launch_T<256>(c, *p, pidx, st, arr, n, stride);
-        case 512: return launch_T<512>(c, *p, pidx, st, arr, n, stride);
         default: return launch_T<64>(c, *p, pidx, st, arr, n, stride);
     }
 }
@@ -549,9 +547,7 @@ int bnp_set_launch_config(int threads_per_block, int phase_mode) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (phase_mode >= 1 && phase_mode <= 3) g_phase_mode = phase_mode - 2;  // 1 automatic, 2 never split, 3 always split
     if (threads_per_block == 0) return BNP_OK;
-    if (threads_per_block != 32 && threads_per_block != 64 && threads_per_block != 96 && threads_per_block != 128 &&
-        threads_per_block != 256 &&
-        threads_per_block != 512)
+    if (threads_per_block != 32 && threads_per_block != 64 && threads_per_block != 128 && threads_per_block != 256)
         return BNP_EINVAL;
     g_threads_per_block = threads_per_block;
     return BNP_OK;

@@ -1,66 +1,69 @@
-// The Fq2 sequencer, component-split: TWO lanes = one pairing, all lanes run the same straight-line program.
+// The Fq2 sequencer: ONE THREAD = ONE PAIRING, every thread of the grid runs the same straight-line program.
 //
 // Why a sequencer instead of one giant inlined kernel (B200-first reasoning):
 //   * a fused pairing is ~27 000 Fq2-level operations; inlined that is >10^7 SASS instructions, far
-//     beyond the instruction caches.  Here every Fq2 operation exists once and stays resident;
-//   * the per-pairing state (f: 384 B, R: 192 B, lines, temporaries) exceeds the register file at any
-//     useful occupancy, and registers cannot be indexed dynamically.  The state lives in shared memory
-//     as Fq2 slots, registers hold only the operands of the running operation;
-//   * control flow is warp- and grid-uniform (the program counter is the same for every thread).
+//     beyond the instruction caches (L0 ~6 KB per scheduler, L1.5 32 KB per SM).  Here every Fq2 operation
+//     exists once and the whole hot path stays inside the L1.5;
+//   * the per-pairing state (f: 384 B, R: 192 B, lines, Karatsuba temporaries) exceeds the register file at any
+//     useful occupancy, and registers cannot be indexed dynamically.  The state lives in shared memory as
+//     64-byte Fq2 slots laid out [slot][quad][thread] (every access a conflict-free LDS.128 / STS.128);
+//     registers hold only the operands of the running operation;
+//   * control flow is grid-uniform: the program counter is the same for every thread, every branch of a handler
+//     is decided by instruction fields, so there is no divergence and no per-lane select anywhere.
 //
-// Why two lanes per pairing (measured, profiles/ncu_r1_attach_phases*.txt): with one thread per pairing the
-// 896 B of slots per thread cap the SM at 8 warps (2 per scheduler) and the kernel sits at 43 % of the
-// IMAD.WIDE pipe with 46 % of its stall samples in fixed-latency waits - there are not enough warps to cover the
-// serial carry chains around the products.  Lane l < 16 of a warp computes component c0 of pairing l of the
-// warp's 16-pairing chunk, lane l + 16 computes c1.  Per lane the slots are 32 bytes, so the same shared
-// memory holds twice the warps (16 per SM, 4 per scheduler), the per-lane register footprint halves, and every
-// Fq2 product becomes a two-term dot product with ONE reduction per lane:
-//       c0 = x0*y0 + x1*(kp - y1)         c1 = x0*y1 + x1*y0
-// (no Karatsuba: 4 wide products instead of 3, but no 512-bit subtractions, no borrow fix-up and a single
-// merge-add; squarings and Fq-scalar products split evenly with no extra work).  A lane reads its partner's
-// component straight from shared memory (layout [slot][quad][thread]: own, partner and broadcast reads are
-// all conflict-free LDS.128); lanes only ever differ in addresses and select masks, never in control flow.
+// Why one thread per pairing (round 2; round 1 shipped a two-lanes-per-pairing component split):
+// measured on B200 with tools/mb/mb2.cu (profiles/mb_r2_solo_probe.txt), a lane that runs a WHOLE Fq2 product
+// (Karatsuba: 3 wide products, 2 reductions, 336 MACs) from shared-memory slots sustains 79-82 % of the IMAD.WIDE
+// pipe at 8 warps per SM and gains nothing from 12 or 14 warps, while the component split paid 4 wide products
+// per Fq2 product plus a partner negate/select and topped out at 72 % of the pipe on executed MACs (62 % on
+// algorithmic ones).  Per Fq2 product the thread-per-pairing form issues ~620 instructions for 32 pairings, the
+// split ~870 for 16 + 16 lanes.  Occupancy is then set by shared memory alone (14 slots x 64 B x 256 threads).
 #pragma once
 #include "fp2.cuh"
 #include "microcode_ops.h"
 
 #define BNP_NARR 6
 #define BNP_MAX_CONST 128
-#define BNP_MAX_PHASES 8
-#define BNP_CHUNK 16  // pairings per warp
+#define BNP_MAX_PHASES 16
+#define BNP_CHUNK 32  // pairings per warp-task
 
 struct VmArgs {
     const u64* prog[BNP_MAX_PHASES];  // instruction words of each phase (device global memory)
     u64* arr[BNP_NARR];     // SoA arrays: [K][4][stride] u64 (ids in microcode/isa.py); arr[5] = phase state
-    uint4* scratch;         // [n_scratch][2][total_threads] uint4
+    uint4* scratch;         // [n_scratch][4][total_threads] uint4
     u32 n;                  // elements to process
     u32 stride;             // elements per limb row of the arrays (>= n)
-    u32* counter;           // work counter (zeroed before launch): warps claim (phase, 16-element chunk) tasks
+    u32* counter;           // work counter (zeroed before launch): warps claim (phase, 32-element chunk) tasks
     u32* progress;          // per chunk: number of completed phases (zeroed before launch; unused when n_phases == 1)
     u32 n_phases;
 };
 
 __device__ __constant__ u32 BNP_CONSTS[BNP_MAX_CONST][16];
 
-// Shared-memory slots.  A lane holds ONE Fq component (32 B = two uint4) of every slot; the two lanes of a
-// pairing are 16 apart in the warp.
+// Shared-memory slots: [slot][quad][thread] uint4; quads 0,1 = c0, quads 2,3 = c1.
 template <int T>
 struct Slots {
-    uint4* h0;  // where component 0 / 1 of this lane's pairing lives (one of them is the lane's own)
-    uint4* h1;
-    uint4* own;
-    uint4* oth;
-    __device__ __forceinline__ const uint4* half(u32 k) const { return k ? h1 : h0; }
-    __device__ __forceinline__ void load(u32* r, const uint4* base, u32 s) const {
-        const uint4* p = base + s * (2 * T);
+    uint4* base;  // already offset by threadIdx.x
+    __device__ __forceinline__ void load_half(u32* r, u32 s, u32 half) const {
+        const uint4* p = base + s * (4 * T) + half * (2 * T);
         uint4 q0 = p[0], q1 = p[T];
         r[0] = q0.x; r[1] = q0.y; r[2] = q0.z; r[3] = q0.w;
         r[4] = q1.x; r[5] = q1.y; r[6] = q1.z; r[7] = q1.w;
     }
-    __device__ __forceinline__ void store(u32 s, const u32* r) const {
-        uint4* p = own + s * (2 * T);
-        p[0] = make_uint4(r[0], r[1], r[2], r[3]);
-        p[T] = make_uint4(r[4], r[5], r[6], r[7]);
+    __device__ __forceinline__ void load(Fp2& r, u32 s) const {
+        const uint4* p = base + s * (4 * T);
+        uint4 q0 = p[0], q1 = p[T], q2 = p[2 * T], q3 = p[3 * T];
+        r.c0[0] = q0.x; r.c0[1] = q0.y; r.c0[2] = q0.z; r.c0[3] = q0.w;
+        r.c0[4] = q1.x; r.c0[5] = q1.y; r.c0[6] = q1.z; r.c0[7] = q1.w;
+        r.c1[0] = q2.x; r.c1[1] = q2.y; r.c1[2] = q2.z; r.c1[3] = q2.w;
+        r.c1[4] = q3.x; r.c1[5] = q3.y; r.c1[6] = q3.z; r.c1[7] = q3.w;
+    }
+    __device__ __forceinline__ void store(u32 s, const Fp2& r) const {
+        uint4* p = base + s * (4 * T);
+        p[0] = make_uint4(r.c0[0], r.c0[1], r.c0[2], r.c0[3]);
+        p[T] = make_uint4(r.c0[4], r.c0[5], r.c0[6], r.c0[7]);
+        p[2 * T] = make_uint4(r.c1[0], r.c1[1], r.c1[2], r.c1[3]);
+        p[3 * T] = make_uint4(r.c1[4], r.c1[5], r.c1[6], r.c1[7]);
     }
 };
 
@@ -81,90 +84,43 @@ __device__ __forceinline__ void stg_fp(u64* arr, u32 f, u32 n, u32 e, const u32*
     for (int j = 0; j < 4; j++) p[(size_t)j * n] = (u64)r[2 * j] | ((u64)r[2 * j + 1] << 32);
 }
 
-// r = sel ? a : b, limb-wise (sel is per lane: never a branch)
-__device__ __forceinline__ void sel8(u32* r, bool sel, const u32* a, const u32* b) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) r[i] = sel ? a[i] : b[i];
-}
-
-// 512-bit r = a + b (no carry out by the callers' bounds)
-__device__ __forceinline__ void add16(u32* r, const u32* a, const u32* b) {
-    asm("add.cc.u32  %0, %16, %32;\n\t"
-        "addc.cc.u32 %1, %17, %33;\n\t"
-        "addc.cc.u32 %2, %18, %34;\n\t"
-        "addc.cc.u32 %3, %19, %35;\n\t"
-        "addc.cc.u32 %4, %20, %36;\n\t"
-        "addc.cc.u32 %5, %21, %37;\n\t"
-        "addc.cc.u32 %6, %22, %38;\n\t"
-        "addc.cc.u32 %7, %23, %39;\n\t"
-        "addc.cc.u32 %8, %24, %40;\n\t"
-        "addc.cc.u32 %9, %25, %41;\n\t"
-        "addc.cc.u32 %10, %26, %42;\n\t"
-        "addc.cc.u32 %11, %27, %43;\n\t"
-        "addc.cc.u32 %12, %28, %44;\n\t"
-        "addc.cc.u32 %13, %29, %45;\n\t"
-        "addc.cc.u32 %14, %30, %46;\n\t"
-        "addc.u32    %15, %31, %47;"
-        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]),
-          "=&r"(r[8]), "=&r"(r[9]), "=&r"(r[10]), "=&r"(r[11]), "=&r"(r[12]), "=&r"(r[13]), "=&r"(r[14]), "=&r"(r[15])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8]),
-          "r"(a[9]), "r"(a[10]), "r"(a[11]), "r"(a[12]), "r"(a[13]), "r"(a[14]), "r"(a[15]), "r"(b[0]), "r"(b[1]),
-          "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(b[8]), "r"(b[9]), "r"(b[10]),
-          "r"(b[11]), "r"(b[12]), "r"(b[13]), "r"(b[14]), "r"(b[15]));
-}
-
-// r = k p - a, k = 1 or 2 (a <= k p); `two` is warp-uniform (an instruction flag), the constants are immediates
-__device__ __forceinline__ void fp_kp_minus(u32* r, const u32* a, bool two) {
-    if (two) {
-        const u32 p2[8] = {0xb0f9fa8eu, 0x7841182du, 0xd0e3951au, 0x2f02d522u, 0x0302b0bbu, 0x70a08b6du, 0xc2634053u, 0x60c89ce5u};
-        sub8(r, p2, a);
-    } else {
-        fp_p_minus(r, a);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
-// LIN engine, one output component per lane:
-//     out = sum_j mult_j * (neg_j ? p - z_j : z_j)  <  1024 p,  reduced once by a quotient estimate.
-// An entry is one pair of 4-deep IMAD.WIDE chains into 64-bit-column accumulators (E: even limb positions,
-// O: odd).  Entries are 16 bits, [slot:8][half:1][neg:1][mult:6], and come in (component 0, component 1)
-// pairs - a lane takes the entry of its own component, so the two lanes of a pairing differ only in the slot
-// address, the negate select and the multiplier.  One pair per 32-bit word, fetched through the read-only cache
-// one iteration ahead (the loop is software-pipelined by hand); the negate-select is skipped for pairs in which
-// neither lane negates (a warp-uniform test).
+// LIN engine:  out_c = sum_j mult_j * (neg_j ? p - z_j : z_j)  <  1024 p  for c = 0, 1, each reduced once by a
+// quotient estimate.  An entry is one pair of 4-deep IMAD.WIDE chains into 64-bit-column accumulators (E: even limb
+// positions, O: odd).  Entries are 16 bits, [slot:8][half:1][neg:1][mult:6], and come in (component 0, component 1)
+// pairs, one pair per 32-bit word; the two components are independent chains the scheduler interleaves.  A pair is
+// fetched one iteration ahead of its use (the loop is software-pipelined by hand); multiplier 0 pads the shorter
+// list.  Every test below is warp-uniform.
 // ---------------------------------------------------------------------------------------------
-#define BNP_LIN_FETCH(J, Z, TT, NG)                                           \
+#define BNP_LIN_FETCH(J, ZA, ZB, TT)                                          \
     {                                                                         \
-        const u32 t_ = __ldg(ents + (J));      /* one (component 0, component 1) pair, same word for every lane */ \
-        NG = (t_ & 0x02000200u) != 0u;         /* warp-uniform: does either lane negate? */                        \
-        TT = comp ? (t_ >> 16) : (t_ & 0xffffu);                              \
-        S.load(Z, S.half((TT >> 8) & 1u), TT & 0xffu);                        \
+        TT = __ldg(ents + (J));                                               \
+        S.load_half(ZA, TT & 0xffu, (TT >> 8) & 1u);                          \
+        S.load_half(ZB, (TT >> 16) & 0xffu, (TT >> 24) & 1u);                 \
     }
-#define BNP_LIN_ACC(Z, TT, NG)                                                \
+#define BNP_LIN_ACC(ZA, ZB, TT)                                               \
     {                                                                         \
-        if (NG) {                                                             \
-            u32 nz_[8];                                                       \
-            fp_p_minus(nz_, Z);                                               \
-            sel8(Z, (TT & 0x200u) != 0u, nz_, Z);                             \
-        }                                                                     \
-        chain_acc64(E, TT >> 10, Z[0], Z[2], Z[4], Z[6]);                     \
-        chain_acc64(O, TT >> 10, Z[1], Z[3], Z[5], Z[7]);                     \
+        if (TT & 0x00000200u) fp_p_minus(ZA, ZA);                             \
+        if (TT & 0x02000000u) fp_p_minus(ZB, ZB);                             \
+        const u32 ma_ = (TT >> 10) & 63u, mb_ = TT >> 26;                     \
+        chain_acc64(E0, ma_, ZA[0], ZA[2], ZA[4], ZA[6]);                     \
+        chain_acc64(O0, ma_, ZA[1], ZA[3], ZA[5], ZA[7]);                     \
+        chain_acc64(E1, mb_, ZB[0], ZB[2], ZB[4], ZB[6]);                     \
+        chain_acc64(O1, mb_, ZB[1], ZB[3], ZB[5], ZB[7]);                     \
     }
-
-// first entry of a LIN: the accumulators are written, not accumulated into (no zero-initialisation)
-#define BNP_LIN_ACC_FIRST(Z, TT, NG)                                          \
+// first pair of a LIN: the accumulators are written, not accumulated into (no zero-initialisation)
+#define BNP_LIN_ACC_FIRST(ZA, ZB, TT)                                         \
     {                                                                         \
-        if (NG) {                                                             \
-            u32 nz_[8];                                                       \
-            fp_p_minus(nz_, Z);                                               \
-            sel8(Z, (TT & 0x200u) != 0u, nz_, Z);                             \
-        }                                                                     \
-        const u32 m_ = TT >> 10;                                              \
+        if (TT & 0x00000200u) fp_p_minus(ZA, ZA);                             \
+        if (TT & 0x02000000u) fp_p_minus(ZB, ZB);                             \
+        const u32 ma_ = (TT >> 10) & 63u, mb_ = TT >> 26;                     \
         _Pragma("unroll") for (int c_ = 0; c_ < 4; c_++) {                    \
-            E[c_] = (u64)m_ * Z[2 * c_];                                      \
-            O[c_] = (u64)m_ * Z[2 * c_ + 1];                                  \
+            E0[c_] = (u64)ma_ * ZA[2 * c_];                                   \
+            O0[c_] = (u64)ma_ * ZA[2 * c_ + 1];                               \
+            E1[c_] = (u64)mb_ * ZB[2 * c_];                                   \
+            O1[c_] = (u64)mb_ * ZB[2 * c_ + 1];                               \
         }                                                                     \
-        E[4] = O[4] = 0ull;                                                   \
+        E0[4] = O0[4] = E1[4] = O1[4] = 0ull;                                 \
     }
 
 // v = E + (O << 32): nine limbs (the total is below 2^264, so limb 9 of either part is zero)
@@ -192,109 +148,113 @@ __device__ __forceinline__ void lin_merge(u32* v, const u64* Ec, const u64* Oc) 
 }
 
 template <int T>
-__device__ __forceinline__ void vm_lin(const Slots<T>& S, bool comp, u32* out, u32 n, const u64* more) {
+__device__ __forceinline__ void vm_lin(const Slots<T>& S, Fp2& out, u32 n, const u64* more) {
     const u32* ents = (const u32*)more;  // pair j is the j-th 32-bit word of the entry list
-    u64 E[5], O[5];
-#ifndef BNP_LIN_SINGLE_COPY
-    u32 za[8], ya[8], ta, ua;
-    bool na, nu;
-    BNP_LIN_FETCH(0u, za, ta, na);
-    if (1u < n) BNP_LIN_FETCH(1u, ya, ua, nu);
-    BNP_LIN_ACC_FIRST(za, ta, na);
+    u64 E0[5], O0[5], E1[5], O1[5];
+#ifdef BNP_LIN_PIPELINED
+    // hand-pipelined form (three copies of the entry body: +3 KB of hot code)
+    u32 za[8], zb[8], ya[8], yb[8], ta, ua;
+    BNP_LIN_FETCH(0u, za, zb, ta);
+    if (1u < n) BNP_LIN_FETCH(1u, ya, yb, ua);
+    BNP_LIN_ACC_FIRST(za, zb, ta);
 #pragma unroll 1
-    for (u32 j = 1; j < n; j += 2u) {   // ya holds pair j
-        if (j + 1u < n) BNP_LIN_FETCH(j + 1u, za, ta, na);
-        BNP_LIN_ACC(ya, ua, nu);
+    for (u32 j = 1; j < n; j += 2u) {   // (ya, yb) hold pair j
+        if (j + 1u < n) BNP_LIN_FETCH(j + 1u, za, zb, ta);
+        BNP_LIN_ACC(ya, yb, ua);
         if (j + 1u >= n) break;
-        if (j + 2u < n) BNP_LIN_FETCH(j + 2u, ya, ua, nu);
-        BNP_LIN_ACC(za, ta, na);
+        if (j + 2u < n) BNP_LIN_FETCH(j + 2u, ya, yb, ua);
+        BNP_LIN_ACC(za, zb, ta);
     }
 #else
-    // one copy of the entry body: 56 instructions smaller, measured 0.5 % slower than the hand-pipelined form above
 #pragma unroll
-    for (int i = 0; i < 5; i++) E[i] = O[i] = 0ull;
+    for (int i = 0; i < 5; i++) E0[i] = O0[i] = E1[i] = O1[i] = 0ull;
 #pragma unroll 1
     for (u32 j = 0; j < n; j++) {
-        u32 za[8], ta;
-        bool na;
-        BNP_LIN_FETCH(j, za, ta, na);
-        BNP_LIN_ACC(za, ta, na);
+        u32 za[8], zb[8], ta;
+        BNP_LIN_FETCH(j, za, zb, ta);
+        BNP_LIN_ACC(za, zb, ta);
     }
 #endif
-    u32 v[9];
-    lin_merge(v, E, O);
-    fp_reduce_lazy(out, v);
+    u32 v0[9], v1[9];
+    lin_merge(v0, E0, O0);
+    lin_merge(v1, E1, O1);
+    fp_reduce_lazy(out.c0, v0);
+    fp_reduce_lazy(out.c1, v1);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Product class (MUL / SQR / MULFP), one shared body:
-//   T = this lane's wide value;  T += 2^256 * hi terms;  r' = canon(redc(T));  [S[d] = r'];  [S[d2] = LIN(r', ...)]
+// Product class (MUL / SQR / MULFP), one shared tail:
+//   (T0, T1) = the two wide components;  T += 2^256 * hi terms;  r' = canon(redc(T));  [S[d] = r'];  [S[d2] = LIN(r', ...)]
 // On entry `pc` points at the word after the instruction; on exit `ins` holds the next instruction
 // and `pc` points past it.
 // ---------------------------------------------------------------------------------------------
 template <int T>
-__device__ __forceinline__ void vm_product(const Slots<T>& S, bool comp, u32 op, const u64*& pc, u64& ins, u32 d, u32 a,
-                                           u32 b, u32 c, u32 ee, u32 imm) {
+__device__ __forceinline__ void vm_product(const Slots<T>& S, u32 op, const u64*& pc, u64& ins, u32 d, u32 a, u32 b, u32 c,
+                                           u32 ee, u32 imm) {
     const u64* p0 = pc;
     const u64 w0 = __ldg(p0), w1 = __ldg(p0 + 1);  // extension word (or the next instruction), the word after it
-    // Every product-class opcode is  T = u1 * v1 [+ u2 * v2]  followed by the same tail; only the operand
-    // preparation differs, so the wide products, the reduction and the epilogue exist ONCE in the instruction
-    // stream (the kernel is instruction-fetch sensitive: L0 is ~6 KB per scheduler, L1.5 32 KB per SM).
-    u32 u1[8], v1[8], u2[8], v2[8];
+    // Every product-class opcode starts with the same TWO independent wide products A = u0 * v0, B = u1 * v1
+    // (one copy of that code in the instruction stream: the hot path has to stay inside the 32 KB L1.5):
+    //   MUL:    A = x0 y0, B = x1 y1, then C = (x0 + x1)(y0 + y1);  T0 = A - B (+ p 2^256 if negative), T1 = C - A - B
+    //   SQR:    T0 = (x0 + x1)(x0 - x1), T1 = (2 x0) x1
+    //   MULFP:  T0 = x0 s, T1 = x1 s
+    u32 T0[16], T1[16];
+    u32 u0[8], v0[8], u1[8], v1[8], sx[8], sy[8];
     if (op == BNP_OP_MUL) {
-        // lane c:  x0 * y[c]  +  x1 * (c ? y0 : k p - y1)
-        S.load(u1, S.h0, a);
-        S.load(u2, S.h1, a);
-        S.load(v1, S.own, c);
-        S.load(v2, S.oth, c);
+        Fp2 x, y;
+        S.load(x, a);
+        S.load(y, c);
         if (imm & (BNP_MUL_B | BNP_MUL_E)) {  // Karatsuba-level operands: (a +- b) * (c +- e), sums kept lazy (< 2p)
-            u32 t[8];
+            Fp2 t;
             if (imm & BNP_MUL_B) {
-                S.load(t, S.h0, b);
-                if (imm & BNP_MUL_BNEG) fp_sub_lazy(u1, u1, t); else add8(u1, u1, t);
-                S.load(t, S.h1, b);
-                if (imm & BNP_MUL_BNEG) fp_sub_lazy(u2, u2, t); else add8(u2, u2, t);
+                S.load(t, b);
+                if (imm & BNP_MUL_BNEG) fp2_sub_lazy(x, x, t); else fp2_add_lazy(x, x, t);
                 if (imm & BNP_MUL_BCANON) {
-                    fp_cond_sub_p(u1);
-                    fp_cond_sub_p(u2);
+                    fp_cond_sub_p(x.c0);
+                    fp_cond_sub_p(x.c1);
                 }
             }
             if (imm & BNP_MUL_E) {
-                S.load(t, S.own, ee);
-                if (imm & BNP_MUL_ENEG) fp_sub_lazy(v1, v1, t); else add8(v1, v1, t);
-                S.load(t, S.oth, ee);
-                if (imm & BNP_MUL_ENEG) fp_sub_lazy(v2, v2, t); else add8(v2, v2, t);
+                S.load(t, ee);
+                if (imm & BNP_MUL_ENEG) fp2_sub_lazy(y, y, t); else fp2_add_lazy(y, y, t);
             }
         }
-        u32 nb[8];
-        fp_kp_minus(nb, v2, (imm & BNP_MUL_E) != 0u);
-        sel8(v2, comp, v2, nb);
+        add8(sx, x.c0, x.c1);  // < 4p < 2^256
+        add8(sy, y.c0, y.c1);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { u0[i] = x.c0[i]; v0[i] = y.c0[i]; u1[i] = x.c1[i]; v1[i] = y.c1[i]; }
     } else if (op == BNP_OP_SQR) {
-        // lane 0: (x0 + x1) * (x0 - x1),  lane 1: (x0 + x0) * x1      (x canonical)
-        u32 x0[8], x1[8];
-        S.load(x0, S.h0, a);
-        S.load(x1, S.h1, a);
+        Fp2 x;
+        S.load(x, a);
         if (imm & BNP_MUL_B) {
-            u32 t[8];
-            S.load(t, S.h0, b);
-            if (imm & BNP_MUL_BNEG) fp_sub(x0, x0, t); else fp_add(x0, x0, t);
-            S.load(t, S.h1, b);
-            if (imm & BNP_MUL_BNEG) fp_sub(x1, x1, t); else fp_add(x1, x1, t);
+            Fp2 t;
+            S.load(t, b);
+            if (imm & BNP_MUL_BNEG) fp2_sub(x, x, t); else fp2_add(x, x, t);
         }
-        u32 s[8], dd[8];
-        sel8(s, comp, x0, x1);
-        add8(u1, x0, s);
-        fp_sub(dd, x0, x1);
-        sel8(v1, comp, x1, dd);
+        add8(u0, x.c0, x.c1);
+        fp_sub(v0, x.c0, x.c1);
+        add8(u1, x.c0, x.c0);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { v1[i] = x.c1[i]; sx[i] = sy[i] = 0u; }
     } else {
-        S.load(u1, S.own, a);
-        S.load(v1, S.half(imm & BNP_MULFP_HALF), b);
+        Fp2 x;
+        S.load(x, a);
+        S.load_half(v0, b, (imm & BNP_MULFP_HALF) ? 1u : 0u);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { u0[i] = x.c0[i]; u1[i] = x.c1[i]; v1[i] = v0[i]; sx[i] = sy[i] = 0u; }
     }
-    u32 TT[16];
-    if (op == BNP_OP_MUL)
-        fp_mul2_wide(TT, u1, v1, u2, v2);  // both terms in one pair of column accumulators (v1, v2 <= 2p)
-    else
-        fp_mul_wide(TT, u1, v1);
+    fp_mul_wide(T0, u0, v0);
+    fp_mul_wide(T1, u1, v1);
+    if (op == BNP_OP_MUL) {
+        u32 P2[16];
+        fp_mul_wide(P2, sx, sy);
+        sub16(P2, P2, T0);
+        sub16(P2, P2, T1);
+        const u32 borrow = sub16(T0, T0, T1);
+        add_p_masked(T0 + 8, borrow);
+#pragma unroll
+        for (int i = 0; i < 16; i++) T1[i] = P2[i];
+    }
     u32 np = 0, d2 = 0;  // np: entry pairs of the post LIN
     bool store_r = true;
     if (imm & BNP_MUL_EXT) {
@@ -306,18 +266,21 @@ __device__ __forceinline__ void vm_product(const Slots<T>& S, bool comp, u32 op,
         const u32 n_hi = hflags & 3u;
 #pragma unroll 1
         for (u32 i = 0; i < n_hi; i++) {
-            u32 h[8];
-            S.load(h, S.own, (xl >> (8u * (i + 1u))) & 0xffu);
-            if (hflags & (4u << i)) fp_p_minus(h, h);
-            wide_add_hi(TT, h);
+            Fp2 h;
+            S.load(h, (xl >> (8u * (i + 1u))) & 0xffu);
+            if (hflags & (4u << i)) {
+                fp_p_minus(h.c0, h.c0);
+                fp_p_minus(h.c1, h.c1);
+            }
+            wide_add_hi(T0, h.c0);
+            wide_add_hi(T1, h.c1);
         }
     }
-    u32 r[8];
-    fp_redc_lazy(r, TT);
-    // the two components of a product have the same bound, but take the larger level so the ladder is uniform
-    const u32 l0 = (imm >> BNP_MUL_CANON_SHIFT) & 3u, l1 = (imm >> (BNP_MUL_CANON_SHIFT + 2)) & 3u;
-    fp_canon(r, l0 > l1 ? l0 : l1);
-    __syncwarp();  // every lane has read its operands (a destination may alias a source slot)
+    Fp2 r;
+    fp_redc_lazy(r.c0, T0);
+    fp_redc_lazy(r.c1, T1);
+    fp_canon(r.c0, (imm >> BNP_MUL_CANON_SHIFT) & 3u);
+    fp_canon(r.c1, (imm >> (BNP_MUL_CANON_SHIFT + 2)) & 3u);
     if (!(imm & BNP_MUL_EXT)) {
         S.store(d, r);
         ins = w0;
@@ -326,91 +289,50 @@ __device__ __forceinline__ void vm_product(const Slots<T>& S, bool comp, u32 op,
     }
     if (np) {
         // Post stage: park r' where the entries expect it, then run the LIN engine on the entry list.
-#ifdef BNP_POST_LIN_REDISPATCH
-        // (hand the entry list to the LIN handler of the main loop as a synthetic "LIN d2, np" instruction: one copy
-        //  of the engine in the instruction stream, one more decode per post stage - measured 1.1 % slower)
-        S.store(store_r ? d : d2, r);
-        ins = (u64)BNP_OP_LIN | ((u64)d2 << 8) | ((u64)np << 16);
-        pc = p0 + 1;
-        return;
-#else
         const u32 nw = (np + 1u) >> 1;
         const u64 nx = __ldg(p0 + 1 + nw);
         S.store(store_r ? d : d2, r);
-        __syncwarp();
-        u32 o[8];
-        vm_lin<T>(S, comp, o, np, p0 + 1);
-        __syncwarp();
+        Fp2 o;
+        vm_lin<T>(S, o, np, p0 + 1);
         S.store(d2, o);
         ins = nx;
         pc = p0 + 2 + nw;
         return;
-#endif
     }
     S.store(d, r);
     ins = w1;
     pc = p0 + 2;
 }
 
-#ifndef BNP_LS_MIN
-#define BNP_LS_MIN 128  // blocks of at least this many threads run in lockstep (see below)
-#endif
 #ifndef BNP_MINB
-#define BNP_MINB 8  // resident blocks of 64 threads per SM the register allocation must allow (16 warps: <= 128 registers)
+#define BNP_MINB 4  // resident blocks of 64 threads per SM the register allocation must allow (8 warps: up to 255 registers)
 #endif
 
-// LOCKSTEP (blocks of >= 256 threads): the warps of a block run the program instruction by instruction behind a
-// block barrier.  The handlers are long straight-line code (a product body is ~7 KB against a ~6 KB L0
-// instruction cache per scheduler and 32 KB L1.5 per SM): with free-running warps every warp streams its own
-// copy of the code through the instruction caches and the kernel becomes instruction-fetch bound (measured:
-// 20 % of all stall samples are "no instruction", 72 % of them on the first instruction of a 128-byte line).
-// In lockstep the four warps of a scheduler execute the same lines at nearly the same time, so a line is
-// fetched once per scheduler instead of once per warp.
 template <int T>
-__global__ void __launch_bounds__(T, (T == 96) ? 6 : (BNP_MINB * 64) / T) bnp_vm_kernel(VmArgs args) {
-    constexpr bool LS = T >= BNP_LS_MIN;
-    constexpr u32 WPB = T / 32;
+__global__ void __launch_bounds__(T, (BNP_MINB * 64) / T) bnp_vm_kernel(VmArgs args) {
     extern __shared__ uint4 bnp_smem[];
-    __shared__ u32 s_task;
     const u32 lane = threadIdx.x & 31u;
-    const u32 warp = threadIdx.x >> 5;
-    const bool comp = (lane & 16u) != 0u;
     Slots<T> S;
-    S.h0 = bnp_smem + (threadIdx.x & ~16u);
-    S.h1 = bnp_smem + (threadIdx.x | 16u);
-    S.own = bnp_smem + threadIdx.x;
-    S.oth = bnp_smem + (threadIdx.x ^ 16u);
+    S.base = bnp_smem + threadIdx.x;
     const u32 total = gridDim.x * T;
     const u32 gtid = blockIdx.x * T + threadIdx.x;
     uint4* scr = args.scratch + gtid;
     const u32 n = args.n, stride = args.stride;
 
-    // Persistent warps (blocks in lockstep mode): each claims the next task when it finishes one.  A task is one
-    // phase of the program over one chunk of 16 elements (lockstep: over WPB consecutive chunks, one per warp),
-    // handed out breadth-first (every chunk's phase 0, then every chunk's phase 1, ...), so that only the last
-    // phase of a batch runs on a partly filled machine.  Phase p of a chunk waits for phase p-1 of the same
-    // chunk, which was claimed earlier by a warp that never waits on anything later - so the wait cannot
+    // Persistent warps: each claims the next task when it finishes one.  A task is one phase of the program over one
+    // chunk of 32 elements, handed out breadth-first (every chunk's phase 0, then every chunk's phase 1, ...), so
+    // that only the last phase of a batch runs on a partly filled machine.  Phase p of a chunk waits for phase p-1
+    // of the same chunk, which was claimed earlier by a warp that never waits on anything later - so the wait cannot
     // deadlock and is almost never taken.
     const u32 n_chunks = (n + (BNP_CHUNK - 1u)) / BNP_CHUNK;
-    const u32 n_groups = LS ? (n_chunks + WPB - 1u) / WPB : n_chunks;
-    const u32 n_tasks = n_groups * args.n_phases;
+    const u32 n_tasks = n_chunks * args.n_phases;
     for (;;) {
         u32 task = 0;
-        if (LS) {
-            __syncthreads();
-            if (threadIdx.x == 0) s_task = atomicAdd(args.counter, 1u);
-            __syncthreads();
-            task = s_task;
-        } else {
-            if (lane == 0) task = atomicAdd(args.counter, 1u);
-            task = __shfl_sync(0xffffffffu, task, 0);
-        }
+        if (lane == 0) task = atomicAdd(args.counter, 1u);
+        task = __shfl_sync(0xffffffffu, task, 0);
         if (task >= n_tasks) break;
-        const u32 phase = task / n_groups;
-        const u32 grp = task - phase * n_groups;
-        const u32 chunk_raw = LS ? grp * WPB + warp : grp;
-        const bool chunk_ok = chunk_raw < n_chunks;
-        const u32 chunk = chunk_ok ? chunk_raw : n_chunks - 1u;  // a warp without a chunk shadows the last one and never stores
+        const u32 phase = task / n_chunks;
+        const u32 chunk = task - phase * n_chunks;
         if (phase) {
             if (lane == 0) {
                 u32 done;
@@ -422,8 +344,8 @@ __global__ void __launch_bounds__(T, (T == 96) ? 6 : (BNP_MINB * 64) / T) bnp_vm
             }
             __syncwarp();
         }
-        const u32 e_raw = chunk * BNP_CHUNK + (lane & 15u);
-        const bool active = chunk_ok && e_raw < n;
+        const u32 e_raw = chunk * BNP_CHUNK + lane;
+        const bool active = e_raw < n;
         const u32 e = active ? e_raw : n - 1;  // idle lanes shadow the last element and never store
         const u64* pc = args.prog[0];
 #pragma unroll
@@ -435,105 +357,101 @@ __global__ void __launch_bounds__(T, (T == 96) ? 6 : (BNP_MINB * 64) / T) bnp_vm
             const u32 op = lo & 0xffu, d = (lo >> 8) & 0xffu, a = (lo >> 16) & 0xffu, b = lo >> 24;
             const u32 c = hi & 0xffu, ee = (hi >> 8) & 0xffu, imm = hi >> 16;
             if (op == BNP_OP_END) break;
-            if (LS) __syncthreads(); else __syncwarp();  // the previous instruction's stores are visible to the partner lane
-            // (A straight-line fast path for flag-free MUL/SQR was measured and removed: +10 KB of hot code pushed the
-            //  working set past the 32 KB L1.5 instruction cache, -8 % free-running, no gain in lockstep.)
             if (op == BNP_OP_MUL || op == BNP_OP_SQR || op == BNP_OP_MULFP) {
-                vm_product<T>(S, comp, op, pc, ins, d, a, b, c, ee, imm);
+                vm_product<T>(S, op, pc, ins, d, a, b, c, ee, imm);
                 continue;
             }
             if (op == BNP_OP_LIN) {  // d = LIN(slots), a = number of entry pairs
                 const u32 nw = (a + 1u) >> 1;
                 const u64 nx = __ldg(pc + nw);
-                u32 o[8];
-                vm_lin<T>(S, comp, o, a, pc);
-                __syncwarp();
+                Fp2 o;
+                vm_lin<T>(S, o, a, pc);
                 S.store(d, o);
                 ins = nx;
                 pc += nw + 1;
                 continue;
             }
             const u64 nxt = __ldg(pc++);  // prefetch (every program ends with END followed by padding)
-            u32 x[8], y[8], r[8];
+            Fp2 x, y, r;
             switch (op) {
                 case BNP_OP_LDC:
 #pragma unroll
-                    for (int i = 0; i < 8; i++) r[i] = comp ? BNP_CONSTS[imm][8 + i] : BNP_CONSTS[imm][i];
+                    for (int i = 0; i < 8; i++) {
+                        r.c0[i] = BNP_CONSTS[imm][i];
+                        r.c1[i] = BNP_CONSTS[imm][8 + i];
+                    }
                     S.store(d, r);
                     break;
                 case BNP_OP_LDG:
-                    ldg_fp(r, args.arr[imm], comp ? b : a, stride, e);
+                    ldg_fp(r.c0, args.arr[imm], a, stride, e);
+                    ldg_fp(r.c1, args.arr[imm], b, stride, e);
                     S.store(d, r);
                     break;
                 case BNP_OP_STG:
-                    S.load(x, S.own, a);
-                    if (active) stg_fp(args.arr[imm], comp ? b : d, stride, e, x);
+                    S.load(x, a);
+                    if (active) {
+                        stg_fp(args.arr[imm], d, stride, e, x.c0);
+                        stg_fp(args.arr[imm], b, stride, e, x.c1);
+                    }
                     break;
                 case BNP_OP_SPILL: {
-                    const uint4* p = S.own + a * (2 * T);
-                    uint4* q = scr + (size_t)imm * 2 * total;
+                    const uint4* p = S.base + a * (4 * T);
+                    uint4* q = scr + (size_t)imm * 4 * total;
                     q[0] = p[0];
                     q[total] = p[T];
+                    q[2 * (size_t)total] = p[2 * T];
+                    q[3 * (size_t)total] = p[3 * T];
                     break;
                 }
                 case BNP_OP_FILL: {
-                    uint4* p = S.own + d * (2 * T);
-                    const uint4* q = scr + (size_t)imm * 2 * total;
+                    uint4* p = S.base + d * (4 * T);
+                    const uint4* q = scr + (size_t)imm * 4 * total;
                     // read-once data: bypass L1 (what little L1 the slots leave holds the instruction words)
-                    p[0] = __ldcg(q);
-                    p[T] = __ldcg(q + total);
+                    const uint4 q0 = __ldcg(q), q1 = __ldcg(q + total), q2 = __ldcg(q + 2 * (size_t)total),
+                                q3 = __ldcg(q + 3 * (size_t)total);
+                    p[0] = q0;
+                    p[T] = q1;
+                    p[2 * T] = q2;
+                    p[3 * T] = q3;
                     break;
                 }
-                case BNP_OP_INV: {  // once or twice per program: both lanes run the whole Fq2 inversion
-                    Fp2 v, w;
-                    S.load(v.c0, S.h0, a);
-                    S.load(v.c1, S.h1, a);
-                    fp2_inv(w, v);
-                    sel8(r, comp, w.c1, w.c0);
-                    __syncwarp();
+                case BNP_OP_INV:  // once or twice per program
+                    S.load(x, a);
+                    fp2_inv(r, x);
                     S.store(d, r);
                     break;
-                }
                 case BNP_OP_ADD:
-                    S.load(x, S.own, a);
-                    S.load(y, S.own, b);
-                    fp_add(r, x, y);
+                    S.load(x, a);
+                    S.load(y, b);
+                    fp2_add(r, x, y);
                     S.store(d, r);
                     break;
                 case BNP_OP_SUB:
-                    S.load(x, S.own, a);
-                    S.load(y, S.own, b);
-                    fp_sub(r, x, y);
+                    S.load(x, a);
+                    S.load(y, b);
+                    fp2_sub(r, x, y);
                     S.store(d, r);
                     break;
                 case BNP_OP_DBL:
-                    S.load(x, S.own, a);
-                    fp_add(r, x, x);
+                    S.load(x, a);
+                    fp2_add(r, x, x);
                     S.store(d, r);
                     break;
                 case BNP_OP_NEG:
-                    S.load(x, S.own, a);
-                    fp_neg(r, x);
+                    S.load(x, a);
+                    fp2_neg(r, x);
                     S.store(d, r);
                     break;
                 case BNP_OP_CONJ:
-                    S.load(x, S.own, a);
-                    fp_neg(y, x);
-                    sel8(r, comp, y, x);
+                    S.load(x, a);
+                    fp2_conj(r, x);
                     S.store(d, r);
                     break;
-                case BNP_OP_MULXI: {  // (9 + u)(a0 + a1 u): lane 0 = 9 a0 + (p - a1), lane 1 = 9 a1 + a0
-                    u32 v[9];
-                    S.load(x, S.own, a);
-                    S.load(y, S.oth, a);
-                    fp_p_minus(r, y);
-                    sel8(y, comp, y, r);
-                    mul9_add(v, x, y);
-                    fp_reduce_small(r, v);
-                    __syncwarp();
+                case BNP_OP_MULXI:
+                    S.load(x, a);
+                    fp2_mul_xi(r, x);
                     S.store(d, r);
                     break;
-                }
                 default:
                     break;
             }
@@ -542,10 +460,9 @@ __global__ void __launch_bounds__(T, (T == 96) ? 6 : (BNP_MINB * 64) / T) bnp_vm
         if (args.n_phases > 1u) {  // publish: this chunk's state is complete up to and including `phase`
             __threadfence();
             __syncwarp();
-            if (lane == 0 && chunk_ok)
+            if (lane == 0)
                 asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(args.progress + chunk), "r"(phase + 1u) : "memory");
         }
-        __syncwarp();  // slots are reused by the next task
     }
 }
 

@@ -88,7 +88,7 @@ def wide_bounds(op, flags):
     if op == "MUL":
         la = 2 if (flags & isa.MUL_B and not flags & isa.MUL_BCANON) else 1
         lb = 2 if flags & isa.MUL_E else 1
-        return (2 * la * lb * U, 2 * la * lb * U)   # T0 = x0 y0 + x1 (k p - y1), T1 = x0 y1 + x1 y0
+        return (1.0, 2 * la * lb * U)   # T0 = x0 y0 - x1 y1 (+ p 2^256 if negative) < p 2^256, T1 = x0 y1 + x1 y0
     if op == "SQR":
         return (2 * U, 2 * U)
     if op == "MULFP":

@@ -135,7 +135,7 @@ def test_ragged_batches_bit_exact(lib, cref, n):
     assert np.array_equal(api.final_exp_soa(m), cref.final_exp(m))
 
 
-@pytest.mark.parametrize("threads", [32, 64, 128, 256, 512])
+@pytest.mark.parametrize("threads", [32, 64, 128, 256])
 @pytest.mark.parametrize("phase_mode", [2, 3])
 def test_every_launch_configuration_bit_exact(lib, cref, threads, phase_mode):
     """Block size (>= 128 threads: the warps of a block run in lockstep behind a block barrier, idle warps shadow the
