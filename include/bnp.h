@@ -79,6 +79,12 @@ int bnp_multi_pairing_batch(const uint64_t* g1, const uint64_t* g2, uint64_t* ou
 int bnp_pairing_product(const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n, int variant);
 /* frobenius_map_native(a, power), any power (reduced mod 12)  (final_exp_native.rs:17). */
 int bnp_frobenius_batch(const uint64_t* in, uint64_t* out, size_t n, size_t power);
+/* pow_native(a, exp)  (final_exp_native.rs:56): a^exp for ANY MyFq12 a (not only cyclotomic ones - the reference's
+ * test_pow feeds a random element, :266-273); exp is `n_limbs` little-endian 64-bit limbs, the same for the whole
+ * batch (the reference's Vec<u64>).  The reference's NAF walk (get_naf, :86-128) with its `res / a` for -1 digits;
+ * a = 0 with a negative digit makes the reference panic (division by zero) - here that element comes back as 0.
+ * exp = 0 returns a itself, like the reference (its accumulator starts at `a` and the loop never starts, :57,83). */
+int bnp_pow_u64_batch(const uint64_t* in, uint64_t* out, size_t n, const uint64_t* exp, size_t n_limbs);
 /* MyFq12 `Mul`: out = a * b element-wise. */
 int bnp_fq12_mul_batch(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
 
@@ -91,6 +97,7 @@ int bnp_final_exp_dev(int device, void* stream, const uint64_t* in, uint64_t* ou
 int bnp_final_exp_witness_dev(int device, void* stream, const uint64_t* in, uint64_t* out /* [60][4][n] */, size_t n);
 int bnp_pairing_dev(int device, void* stream, const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n, int k, int variant);
 int bnp_frobenius_dev(int device, void* stream, const uint64_t* in, uint64_t* out, size_t n, size_t power);
+int bnp_pow_u64_dev(int device, void* stream, const uint64_t* in, uint64_t* out, size_t n, const uint64_t* exp, size_t n_limbs);
 int bnp_fq12_mul_dev(int device, void* stream, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
 /* In-place tree product of n MyFq12 values (buf[12][4][n], destroyed) -> out[12][4][1]. */
 int bnp_fq12_product_dev(int device, void* stream, uint64_t* buf, uint64_t* out, size_t n);

@@ -3,6 +3,10 @@
 Same names, argument order and meaning as the reference's public functions:
 
     miller_loop_native(Q, P)              /root/reference/src/miller_loop_native.rs:320   (G2 first!)
+    pow_native(a, exp)                    /root/reference/src/final_exp_native.rs:56      exp = list of u64 limbs
+    get_naf(exp) / frob_coeffs(index)     /root/reference/src/final_exp_native.rs:86,183  (host-side constants)
+    conjugate_fp2 / neg_conjugate_fp2     /root/reference/src/miller_loop_native.rs:284,291
+    SIX_U_PLUS_2_NAF, BN_X                /root/reference/src/miller_loop_native.rs:314; final_exp_native.rs:15
     multi_miller_loop_native(pairs)       /root/reference/src/miller_loop_native.rs:324   pairs = [(P, Q), ...]
     final_exp_native(a)                   /root/reference/src/final_exp_native.rs:209
     frobenius_map_native(a, power)        /root/reference/src/final_exp_native.rs:17
@@ -139,6 +143,17 @@ def fq12_mul_soa(a, b):
     return out
 
 
+def pow_soa(f, exp):
+    """f ^ exp for every element; exp: list of little-endian u64 limbs (the reference's Vec<u64>), shared by the batch."""
+    lib = native.lib()
+    n = f.shape[2]
+    out = np.empty((12, 4, n), dtype=np.uint64)
+    limbs = np.array([int(x) for x in exp], dtype=np.uint64)
+    native.check(lib.bnp_pow_u64_batch(_ptr(f), _ptr(out), n, limbs.ctypes.data_as(ctypes.c_void_p) if len(limbs) else None,
+                                       len(limbs)))
+    return out
+
+
 # ----------------------------------------------------------------------------- batched slice variants (north star)
 def miller_loop_native_batch(Qs, Ps):
     """[miller_loop_native(Q_i, P_i)]"""
@@ -235,6 +250,82 @@ def final_exp_native(a):
 
 def frobenius_map_native(a, power):
     return frobenius_map_native_batch([a], power)[0]
+
+
+def pow_native_batch(fs, exp):
+    if not fs:
+        return []
+    return unpack_soa(pow_soa(pack_soa(fs), exp))
+
+
+def pow_native(a, exp):
+    """final_exp_native.rs:56-84: a^exp for any MyFq12 a, exp = list of u64 limbs (little endian)."""
+    return pow_native_batch([a], exp)[0]
+
+
+# ---- host-side constants of the reference's public API (no device work: these are table generators)
+BN_X = 4965661367192848881                       # final_exp_native.rs:15
+SIX_U_PLUS_2_NAF = [                             # miller_loop_native.rs:314-318
+    0, 0, 0, 1, 0, 1, 0, -1, 0, 0, 1, -1, 0, 0, 1, 0, 0, 1, 1, 0, -1, 0, 0, 1, 0, -1, 0, 0, 0, 0,
+    1, 1, 1, 0, 0, -1, 0, 0, 1, 0, 0, 0, 0, 0, -1, 0, 0, 1, 1, 0, 0, -1, 0, 0, 0, 1, 1, 0, -1, 0,
+    0, 1, 0, 1, 1,
+]
+
+
+def get_naf(exp):
+    """final_exp_native.rs:86-128, statement by statement (exp: list of u64 limbs, least significant first):
+    every limb contributes exactly 64 digits, the carry out of a limb is added into the next one, and a carry out
+    of the top limb appends one more digit - after tripping the reference's own `assert_eq!(len, exp.len() + 1)`
+    (:123), which can never hold there: the reference PANICS on such exponents, and so does this (ValueError)."""
+    exp = [int(x) for x in exp]
+    naf = []
+    length = len(exp)
+    for idx in range(length):
+        e = exp[idx]
+        for _ in range(64):
+            if e & 1:
+                z = 2 - (e % 4)
+                e //= 2
+                if z == -1:
+                    e += 1
+                naf.append(z)
+            else:
+                naf.append(0)
+                e //= 2
+        if e != 0:
+            j = idx + 1
+            while j < len(exp) and exp[j] == (1 << 64) - 1:
+                exp[j] = 0
+                j += 1
+            if j < len(exp):
+                exp[j] += 1
+            else:
+                exp.append(1)
+    if len(exp) != length:
+        raise ValueError("get_naf: carry out of the top limb (the reference panics here, final_exp_native.rs:123)")
+    return naf
+
+
+def frob_coeffs(index):
+    """final_exp_native.rs:183-192: xi^((p^index - 1) / 6) as an Fq2 (c0, c1), xi = 9 + u."""
+    e = (P ** index - 1) // 6
+    r, b = (1, 0), (9, 1)
+    while e:
+        if e & 1:
+            r = ((r[0] * b[0] - r[1] * b[1]) % P, (r[0] * b[1] + r[1] * b[0]) % P)
+        b = ((b[0] * b[0] - b[1] * b[1]) % P, (2 * b[0] * b[1]) % P)
+        e >>= 1
+    return r
+
+
+def conjugate_fp2(x):
+    """miller_loop_native.rs:284-289"""
+    return (x[0] % P, (-x[1]) % P)
+
+
+def neg_conjugate_fp2(x):
+    """miller_loop_native.rs:291-296"""
+    return ((-x[0]) % P, x[1] % P)
 
 
 def pairing(p, q):

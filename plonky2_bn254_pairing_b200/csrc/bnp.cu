@@ -8,8 +8,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <thread>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/bnp.h"
@@ -24,6 +27,10 @@ struct DevCtx {
     int dev = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // host<->device copies of the chunked host-pointer path
+    cudaEvent_t last_launch = nullptr;   // recorded after every kernel launch (see launch_T)
+    cudaStream_t last_stream = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     std::vector<u64*> d_prog;  // one device copy per program
     uint4* scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -33,15 +40,18 @@ struct DevCtx {
     size_t progress_count = 0;
     u32* counters = nullptr;   // ring of work counters, one per launch in flight
     unsigned next_counter = 0;
+    u64* pow_buf[2] = {nullptr, nullptr};  // work buffers of the run-time exponent walk (bnp_pow_u64_*)
+    size_t pow_bytes[2] = {0, 0};
     // staging for the host-pointer API
     u64* stage[BNP_NARR] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t stage_bytes[BNP_NARR] = {0, 0, 0, 0, 0, 0};
 };
 
 std::mutex g_mu;
+std::mutex g_launch_mu;  // serialises launch() between the per-device worker threads of one host-pointer call
 std::vector<DevCtx> g_ctx;
 std::atomic<uint64_t> g_launches{0};
-int g_threads_per_block = 64;  // 4 blocks of 64 threads per SM: 8 resident warps, the shared-memory limit of 14 slots
+int g_threads_per_block = 64;  // blocks of 64 threads: one thread per pairing
 thread_local std::string g_last_error;
 
 int cuda_fail(cudaError_t e, const char* what) {
@@ -71,12 +81,13 @@ DevCtx* find_ctx(int device) {
 
 int g_phase_mode = -1;  // -1: automatic, 0: never split, 1: always split when a split variant exists
 
-// cudaMalloc-backed buffer that only grows; the streams are drained before it is replaced
+// cudaMalloc-backed buffer that only grows; the whole device is drained before it is replaced (a kernel queued on
+// any stream may still be using the old buffer)
 template <typename P>
 int grow(DevCtx& c, cudaStream_t st, P*& buf, size_t& have, size_t need) {
     if (need <= have) return BNP_OK;
-    CK(cudaStreamSynchronize(c.stream));
-    if (st != c.stream) CK(cudaStreamSynchronize(st));
+    (void)st;
+    CK(cudaDeviceSynchronize());
     if (buf) CK(cudaFree(buf));
     buf = nullptr;
     have = 0;
@@ -111,9 +122,18 @@ int launch_T(DevCtx& c, const BnpProgram& p, int pidx, cudaStream_t st, u64* con
     // a thread holds the 64-byte Fq2 value of every slot; BNP_SMEM_PAD (experiments only) lowers the occupancy
     static const size_t pad = std::getenv("BNP_SMEM_PAD") ? (size_t)std::atol(std::getenv("BNP_SMEM_PAD")) : 0;
     const size_t smem = (size_t)slots * 64 * T + pad;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the attribute and the occupancy of a (device, block size, shared memory) triple never change: ask once
+    static std::map<std::tuple<int, int, size_t>, int> occ_cache;
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
+    auto key = std::make_tuple(c.dev, T, smem);
+    auto hit = occ_cache.find(key);
+    if (hit != occ_cache.end()) {
+        per_sm = hit->second;
+    } else {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
+        occ_cache[key] = per_sm;
+    }
     if (per_sm < 1) {
         g_last_error = "program does not fit in shared memory";
         return BNP_EUNSUPPORTED;
@@ -135,6 +155,7 @@ int launch_T(DevCtx& c, const BnpProgram& p, int pidx, cudaStream_t st, u64* con
     const size_t total = blocks * T;
     int rc = grow(c, st, c.scratch, c.scratch_bytes, (size_t)std::max<uint32_t>(scratch, 1) * 64 * total);
     if (rc) return rc;
+    if (c.last_stream != st && c.last_stream != nullptr) CK(cudaStreamWaitEvent(st, c.last_launch, 0));
     VmArgs a;
     for (int i = 0; i < BNP_MAX_PHASES; i++) a.prog[i] = c.d_prog[pidx];
     a.n_phases = 1;
@@ -155,9 +176,13 @@ int launch_T(DevCtx& c, const BnpProgram& p, int pidx, cudaStream_t st, u64* con
     a.n = (u32)n;
     a.stride = (u32)stride;
     a.counter = c.counters + (c.next_counter++ % BNP_NCOUNTERS);
+    // The spill scratch, the phase state and the progress array are ONE per device: launches on different streams
+    // must not overlap.  Every launch records an event; a launch on another stream first waits for the previous one.
     CK(cudaMemsetAsync(a.counter, 0, sizeof(u32), st));
     kern<<<(unsigned)blocks, T, smem, st>>>(a);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(c.last_launch, st));
+    c.last_stream = st;
     g_launches++;
     return BNP_OK;
 }
@@ -195,6 +220,13 @@ int init_device(int dev) {
     CK(cudaGetDeviceProperties(&prop, dev));
     c.sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c.last_launch, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) {
+        CK(cudaEventCreateWithFlags(&c.ev_in[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c.ev_done[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c.ev_out[i], cudaEventDisableTiming));
+    }
     CK(cudaMalloc(&c.counters, BNP_NCOUNTERS * sizeof(u32)));
     if (BNP_NCONST > BNP_MAX_CONST) return BNP_EUNSUPPORTED;
     CK(cudaMemcpyToSymbol(BNP_CONSTS, BNP_CONST_TABLE, (size_t)BNP_NCONST * 64));
@@ -263,6 +295,73 @@ struct HostIn {
     size_t K;
 };
 
+// One device's share [off, off + cnt) of a host-pointer batch, run as a pipeline of sub-batches:
+//     copy stream:   H2D(0)  H2D(1)        H2D(2)        ...            D2H(0)   D2H(1) ...
+//     compute:               K(0)          K(1)          K(2) ...
+// so that the copies of one sub-batch overlap the kernel of another.  With pageable caller memory (a Rust Vec, a numpy
+// array) the driver stages the copies through its own pinned buffers and blocks the issuing host thread for their
+// duration - which is why every device has its own host thread and why the kernel of sub-batch i is queued BEFORE the
+// blocking copy-out of sub-batch i-1.  Sub-batches stay large (>= BNP_PIPE_MIN elements): one launch needs
+// 148 SMs x 12 warps x 32 = 56 832 pairings just to occupy every resident warp once (measured: four sub-batches of
+// 16 384 halve the 2^16 throughput), so batches below 2 x BNP_PIPE_MIN run as a single copy-in / kernel / copy-out.
+#ifndef BNP_PIPE_MIN
+#define BNP_PIPE_MIN 131072
+#endif
+#ifndef BNP_PIPE_MAX_CHUNKS
+#define BNP_PIPE_MAX_CHUNKS 4
+#endif
+
+int run_host_device(DevCtx& c, const char* prog, const std::vector<HostIn>& ins, u64* out, size_t K_out, size_t n,
+                    size_t off, size_t cnt, std::string* err) {
+    auto fail = [&](int rc) {
+        if (err) *err = g_last_error;
+        cudaStreamSynchronize(c.copy_stream);  // nothing may still be touching the caller's buffers on return
+        cudaStreamSynchronize(c.stream);
+        return rc;
+    };
+    if (cudaSetDevice(c.dev) != cudaSuccess) return fail(BNP_ECUDA);
+    const u64* arr[BNP_NARR] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int rc;
+    for (auto& in : ins) {
+        if ((rc = ensure_stage(c, in.which, in.K * 32 * cnt))) return fail(rc);
+        arr[in.which] = c.stage[in.which];
+    }
+    if ((rc = ensure_stage(c, 3, K_out * 32 * cnt))) return fail(rc);
+    size_t n_sub = std::min<size_t>(BNP_PIPE_MAX_CHUNKS, std::max<size_t>(1, cnt / BNP_PIPE_MIN));
+    auto subs = split_range(cnt, n_sub);
+    auto d2h = [&](size_t i) -> int {
+        // device [K_out][4][cnt] columns [subs[i]) -> host [K_out][4][n] columns off + subs[i]
+        if (cudaStreamWaitEvent(c.copy_stream, c.ev_done[i & 1], 0) != cudaSuccess) return BNP_ECUDA;
+        cudaError_t e = cudaMemcpy2DAsync(out + off + subs[i].off, n * 8, c.stage[3] + subs[i].off, cnt * 8,
+                                          subs[i].cnt * 8, K_out * 4, cudaMemcpyDeviceToHost, c.copy_stream);
+        return e == cudaSuccess ? BNP_OK : cuda_fail(e, "cudaMemcpy2DAsync(D2H)");
+    };
+    for (size_t i = 0; i < n_sub; i++) {
+        for (auto& in : ins) {
+            cudaError_t e = cudaMemcpy2DAsync(c.stage[in.which] + subs[i].off, cnt * 8, in.host + off + subs[i].off, n * 8,
+                                              subs[i].cnt * 8, in.K * 4, cudaMemcpyHostToDevice, c.copy_stream);
+            if (e != cudaSuccess) return fail(cuda_fail(e, "cudaMemcpy2DAsync(H2D)"));
+        }
+        if (cudaEventRecord(c.ev_in[i & 1], c.copy_stream) != cudaSuccess) return fail(BNP_ECUDA);
+        if (cudaStreamWaitEvent(c.stream, c.ev_in[i & 1], 0) != cudaSuccess) return fail(BNP_ECUDA);
+        {
+            std::lock_guard<std::mutex> lk(g_launch_mu);  // launch() touches process-wide tables
+            rc = launch(c, prog, nullptr, arr[0] ? arr[0] + subs[i].off : nullptr, arr[1] ? arr[1] + subs[i].off : nullptr,
+                        arr[2] ? arr[2] + subs[i].off : nullptr, arr[4] ? arr[4] + subs[i].off : nullptr,
+                        c.stage[3] + subs[i].off, subs[i].cnt, cnt);
+        }
+        if (rc) return fail(rc);
+        if (cudaEventRecord(c.ev_done[i & 1], c.stream) != cudaSuccess) return fail(BNP_ECUDA);
+        if (i >= 1 && (rc = d2h(i - 1))) return fail(rc);
+    }
+    if ((rc = d2h(n_sub - 1))) return fail(rc);
+    cudaError_t e = cudaStreamSynchronize(c.copy_stream);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "cudaStreamSynchronize"));
+    e = cudaStreamSynchronize(c.stream);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "cudaStreamSynchronize"));
+    return BNP_OK;
+}
+
 int run_host(const char* prog, const std::vector<HostIn>& ins, u64* out, size_t K_out, size_t n) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_ctx.empty()) return BNP_ENODEV;
@@ -271,24 +370,24 @@ int run_host(const char* prog, const std::vector<HostIn>& ins, u64* out, size_t 
         if (!in.host) return BNP_EINVAL;
     if (!out) return BNP_EINVAL;
     auto parts = split_range(n, g_ctx.size());
+    if (g_ctx.size() == 1) return run_host_device(g_ctx[0], prog, ins, out, K_out, n, 0, n, nullptr);
+    // one host thread per device: pageable copies block their issuing thread, and the devices must not serialise
+    std::vector<std::thread> th;
+    std::vector<int> rcs(g_ctx.size(), BNP_OK);
+    std::vector<std::string> errs(g_ctx.size());
     for (size_t d = 0; d < g_ctx.size(); d++) {
         if (parts[d].cnt == 0) continue;
-        DevCtx& c = g_ctx[d];
-        CK(cudaSetDevice(c.dev));
-        const u64* arr[BNP_NARR] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-        for (auto& in : ins) {
-            int rc = copy_in(c, in.which, in.host, in.K, n, parts[d].off, parts[d].cnt);
-            if (rc) return rc;
-            arr[in.which] = c.stage[in.which];
-        }
-        int rc = ensure_stage(c, 3, K_out * 32 * parts[d].cnt);
-        if (rc) return rc;
-        rc = launch(c, prog, nullptr, arr[0], arr[1], arr[2], arr[4], c.stage[3], parts[d].cnt);
-        if (rc) return rc;
-        rc = copy_out(c, 3, out, K_out, n, parts[d].off, parts[d].cnt);
-        if (rc) return rc;
+        th.emplace_back([&, d]() {
+            rcs[d] = run_host_device(g_ctx[d], prog, ins, out, K_out, n, parts[d].off, parts[d].cnt, &errs[d]);
+        });
     }
-    return sync_all();
+    for (auto& t : th) t.join();
+    for (size_t d = 0; d < g_ctx.size(); d++)
+        if (rcs[d]) {
+            g_last_error = errs[d];
+            return rcs[d];
+        }
+    return BNP_OK;
 }
 
 std::string prog_name(const char* base, int k, int variant) {
@@ -310,6 +409,76 @@ int product_dev_locked(DevCtx& c, void* stream, u64* buf, u64* out, size_t n) {
     }
     cudaStream_t st = stream ? (cudaStream_t)stream : c.stream;
     CK(cudaMemcpy2DAsync(out, 8, buf, n * 8, 8, 48, cudaMemcpyDeviceToDevice, st));
+    return BNP_OK;
+}
+
+// get_naf (final_exp_native.rs:86-128): signed digits in {-1, 0, 1}, no two adjacent non-zero, least significant
+// first, of the little-endian multi-limb integer `exp`.
+std::vector<int> naf_digits(const uint64_t* exp, size_t n_limbs) {
+    std::vector<uint64_t> e(exp, exp + n_limbs);
+    e.push_back(0);  // room for the carry of e + 1
+    std::vector<int> out;
+    auto is_zero = [&]() {
+        for (auto v : e)
+            if (v) return false;
+        return true;
+    };
+    while (!is_zero()) {
+        int z = 0;
+        if (e[0] & 1) {
+            z = 2 - (int)(e[0] & 3);  // 1 or -1
+            if (z == 1) {
+                e[0] -= 1;  // e is odd: no borrow
+            } else {
+                for (size_t i = 0; i < e.size(); i++)  // e += 1
+                    if (++e[i] != 0) break;
+            }
+        }
+        out.push_back(z);
+        for (size_t i = 0; i + 1 < e.size(); i++) e[i] = (e[i] >> 1) | (e[i + 1] << 63);
+        e.back() >>= 1;
+    }
+    return out;
+}
+
+// pow_native(a, exp) on device arrays: `in` and `out` are [12][4][n] with row stride n (they may alias).
+// exp == BN_X runs the build-time schedule in one launch; any other exponent walks its NAF digits at run time,
+// one launch per squaring / multiplication (the schedule is the reference's, final_exp_native.rs:56-84: left to
+// right, `res / a` for a -1 digit as a multiplication by a^-1 computed once).
+int pow_dev_locked(DevCtx& c, void* stream, const u64* in, u64* out, size_t n, const uint64_t* exp, size_t n_limbs) {
+    if (n == 0) return BNP_OK;
+    if (n_limbs == 1 && exp[0] == 4965661367192848881ull)
+        return launch(c, "pow_bnx", stream, nullptr, nullptr, in, nullptr, out, n);
+    std::vector<int> naf = naf_digits(exp, n_limbs);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c.stream;
+    if (naf.empty()) {
+        // exponent 0: the reference's loop never starts and returns its initial value `a` itself (final_exp_native.rs:57,83)
+        if (in != out) CK(cudaMemcpyAsync(out, in, 384 * n, cudaMemcpyDeviceToDevice, st));
+        return BNP_OK;
+    }
+    int rc;
+    bool need_inv = false;
+    for (int z : naf) need_inv |= z < 0;
+    // work buffers: the accumulator (ping-pong with `out` is impossible when in == out), a copy of a, and a^-1
+    if ((rc = grow(c, st, c.pow_buf[0], c.pow_bytes[0], 384 * n))) return rc;
+    if ((rc = grow(c, st, c.pow_buf[1], c.pow_bytes[1], 384 * n))) return rc;
+    u64* acc = c.pow_buf[0];
+    u64* inv = c.pow_buf[1];
+    if (need_inv && (rc = launch(c, "fq12_inv", stream, nullptr, nullptr, in, nullptr, inv, n))) return rc;
+    bool started = false;
+    for (size_t i = naf.size(); i-- > 0;) {
+        const int z = naf[i];
+        if (started && (rc = launch(c, "fq12_sqr", stream, nullptr, nullptr, acc, nullptr, acc, n))) return rc;
+        if (z == 0) continue;
+        const u64* m = z > 0 ? in : inv;
+        if (!started) {
+            CK(cudaMemcpyAsync(acc, m, 384 * n, cudaMemcpyDeviceToDevice, st));
+            started = true;
+        } else if ((rc = launch(c, "fq12_mul", stream, nullptr, nullptr, acc, m, acc, n))) {
+            return rc;
+        }
+    }
+    CK(cudaMemcpyAsync(out, acc, 384 * n, cudaMemcpyDeviceToDevice, st));
     return BNP_OK;
 }
 
@@ -350,9 +519,18 @@ void bnp_shutdown(void) {
         if (c.state) cudaFree(c.state);
         if (c.progress) cudaFree(c.progress);
         if (c.counters) cudaFree(c.counters);
+        for (int i = 0; i < 2; i++)
+            if (c.pow_buf[i]) cudaFree(c.pow_buf[i]);
         for (int i = 0; i < BNP_NARR; i++)
             if (c.stage[i]) cudaFree(c.stage[i]);
         cudaStreamDestroy(c.stream);
+        cudaStreamDestroy(c.copy_stream);
+        cudaEventDestroy(c.last_launch);
+        for (int i = 0; i < 2; i++) {
+            cudaEventDestroy(c.ev_in[i]);
+            cudaEventDestroy(c.ev_done[i]);
+            cudaEventDestroy(c.ev_out[i]);
+        }
     }
     g_ctx.clear();
 }
@@ -409,6 +587,25 @@ int bnp_multi_pairing_batch(const uint64_t* g1, const uint64_t* g2, uint64_t* ou
 int bnp_frobenius_batch(const uint64_t* in, uint64_t* out, size_t n, size_t power) {
     std::string name = "frobenius_" + std::to_string(power % 12);
     return run_host(name.c_str(), {{2, in, 12}}, out, 12, n);
+}
+
+int bnp_pow_u64_batch(const uint64_t* in, uint64_t* out, size_t n, const uint64_t* exp, size_t n_limbs) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ctx.empty()) return BNP_ENODEV;
+    if (n == 0) return BNP_OK;
+    if (!in || !out || (n_limbs && !exp)) return BNP_EINVAL;
+    auto parts = split_range(n, g_ctx.size());
+    for (size_t d = 0; d < g_ctx.size(); d++) {
+        if (parts[d].cnt == 0) continue;
+        DevCtx& c = g_ctx[d];
+        CK(cudaSetDevice(c.dev));
+        int rc = copy_in(c, 2, in, 12, n, parts[d].off, parts[d].cnt);
+        if (rc) return rc;
+        if ((rc = ensure_stage(c, 3, 384 * parts[d].cnt))) return rc;
+        if ((rc = pow_dev_locked(c, nullptr, c.stage[2], c.stage[3], parts[d].cnt, exp, n_limbs))) return rc;
+        if ((rc = copy_out(c, 3, out, 12, n, parts[d].off, parts[d].cnt))) return rc;
+    }
+    return sync_all();
 }
 
 int bnp_fq12_mul_batch(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
@@ -511,6 +708,14 @@ int bnp_frobenius_dev(int device, void* stream, const uint64_t* in, uint64_t* ou
     DEV_PROLOGUE
     std::string name = "frobenius_" + std::to_string(power % 12);
     return launch(*c, name.c_str(), stream, nullptr, nullptr, in, nullptr, out, n);
+}
+
+int bnp_pow_u64_dev(int device, void* stream, const uint64_t* in, uint64_t* out, size_t n, const uint64_t* exp,
+                    size_t n_limbs) {
+    DEV_PROLOGUE
+    if (!in || !out || (n_limbs && !exp)) return BNP_EINVAL;
+    CK(cudaSetDevice(c->dev));
+    return pow_dev_locked(*c, stream, in, out, n, exp, n_limbs);
 }
 
 int bnp_fq12_mul_dev(int device, void* stream, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {

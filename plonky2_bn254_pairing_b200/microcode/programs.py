@@ -333,6 +333,39 @@ def prog_fq12_mul(b):
     b.st_fq12(isa.ARR_OUT, b.fq12_mul(b.ld_fq12(isa.ARR_F12), b.ld_fq12(isa.ARR_AUX)))
 
 
+def _pow_naf_general(b, a, e):
+    """pow_native (final_exp_native.rs:56-84) for a build-time exponent and ANY Fq12 input (the reference's own test
+    feeds a non-cyclotomic element, :266-273): left-to-right walk over the NAF digits of `e`, general squarings, and
+    the reference's `res / a` for a -1 digit done as a multiplication by a^-1, computed once (field division is
+    exact, so the bits are the same)."""
+    naf = naf_digits(e)
+    ainv = b.fq12_inv(a) if -1 in naf else None
+    res = None
+    for z in reversed(naf):
+        if res is not None:
+            b.cut()
+            res = b.fq12_sqr(res)
+        if z:
+            m = a if z == 1 else ainv
+            res = m if res is None else b.fq12_mul(res, m)
+    return res
+
+
+def prog_pow_bnx(b):
+    """OUT = F12 ^ BN_X for general F12 (pow_native(a, vec![BN_X]))."""
+    b.st_fq12(isa.ARR_OUT, _pow_naf_general(b, b.ld_fq12(isa.ARR_F12), BN_X))
+
+
+def prog_fq12_sqr(b):
+    """OUT = F12^2 (general element): one step of the run-time exponent walk of bnp_pow_u64_batch."""
+    b.st_fq12(isa.ARR_OUT, b.fq12_sqr(b.ld_fq12(isa.ARR_F12)))
+
+
+def prog_fq12_inv(b):
+    """OUT = 1 / F12 (zero maps to zero; the reference panics on a division by zero)."""
+    b.st_fq12(isa.ARR_OUT, b.fq12_inv(b.ld_fq12(isa.ARR_F12)))
+
+
 OPTEST_OUTPUTS = 36
 
 
@@ -430,6 +463,9 @@ PROGRAMS = [
     ("pairing_v0", prog_pairing, {"variant": 0}),
     ("pairing_v1", prog_pairing, {"variant": 1}),
     ("fq12_mul", prog_fq12_mul, {}),
+    ("fq12_sqr", prog_fq12_sqr, {}),
+    ("fq12_inv", prog_fq12_inv, {}),
+    ("pow_bnx", prog_pow_bnx, {}),
     ("optest", prog_optest, {}),
 ] + [("opbench_" + o.lower(), prog_opbench, {"op": o}) for o in ("MUL", "SQR", "MULFP", "ADD", "SUB", "DBL", "NEG", "MULXI", "LIN4", "LIN4XI", "MULS", "MIX")] \
   + [("frobenius_%d" % k, prog_frobenius, {"power": k}) for k in range(12)] \

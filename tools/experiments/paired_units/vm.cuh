@@ -1,23 +1,33 @@
-// The Fq2 sequencer: ONE THREAD = ONE PAIRING, every thread of the grid runs the same straight-line program.
+// The Fq2 sequencer: every pairing owns one slot file in shared memory and TWO lanes of a warp ("units"); the
+// whole grid runs the same straight-line program of BUNDLES - one Fq2 instruction per unit, same opcode.
 //
 // Why a sequencer instead of one giant inlined kernel (B200-first reasoning):
 //   * a fused pairing is ~27 000 Fq2-level operations; inlined that is >10^7 SASS instructions, far
 //     beyond the instruction caches (L0 ~6 KB per scheduler, L1.5 32 KB per SM).  Here every Fq2 operation
-//     exists once and the whole hot path stays inside the L1.5;
+//     exists once and the hot path stays inside the L1.5;
 //   * the per-pairing state (f: 384 B, R: 192 B, lines, Karatsuba temporaries) exceeds the register file at any
 //     useful occupancy, and registers cannot be indexed dynamically.  The state lives in shared memory as
-//     64-byte Fq2 slots laid out [slot][quad][thread] (every access a conflict-free LDS.128 / STS.128);
+//     64-byte Fq2 slots laid out [slot][quad][pairing] (every access a conflict-free LDS.128 / STS.128);
 //     registers hold only the operands of the running operation;
-//   * control flow is grid-uniform: the program counter is the same for every thread, every branch of a handler
-//     is decided by instruction fields, so there is no divergence and no per-lane select anywhere.
+//   * control flow is grid-uniform: the program counter is the same for every thread and every branch of a
+//     handler is decided by bundle fields that all lanes see.
 //
-// Why one thread per pairing (round 2; round 1 shipped a two-lanes-per-pairing component split):
-// measured on B200 with tools/mb/mb2.cu (profiles/mb_r2_solo_probe.txt), a lane that runs a WHOLE Fq2 product
-// (Karatsuba: 3 wide products, 2 reductions, 336 MACs) from shared-memory slots sustains 79-82 % of the IMAD.WIDE
-// pipe at 8 warps per SM and gains nothing from 12 or 14 warps, while the component split paid 4 wide products
-// per Fq2 product plus a partner negate/select and topped out at 72 % of the pipe on executed MACs (62 % on
-// algorithmic ones).  Per Fq2 product the thread-per-pairing form issues ~620 instructions for 32 pairings, the
-// split ~870 for 16 + 16 lanes.  Occupancy is then set by shared memory alone (14 slots x 64 B x 256 threads).
+// Why two units per pairing, each running a WHOLE Fq2 operation (round 2; measured, profiles/*_r2_*):
+//   * a lane that runs a whole Karatsuba Fq2 product (3 wide products, 2 reductions, 336 MACs) issues ~620
+//     instructions per product; round 1's component split (lane = one Fq component: 4 wide products per Fq2
+//     product, partner negate/select) issued 2 x 435.  Thread-per-pairing cut a 2^16 launch from 16.4 G to 12.8 G
+//     instructions - and ran no faster: the slot file (14 x 64 B) caps an SM at 256 pairings = 8 warps, each warp
+//     is one serial dependency chain (5.3 cycles per issued instruction), and 2 warps per scheduler leave the
+//     IMAD pipe idle during every carry-chain phase (issue slots 37 % used);
+//   * so the parallelism has to come from INSIDE a pairing: the tower arithmetic is full of independent Fq2
+//     operations (18 / 12 / 13 / 9 products in an Fq12 multiplication / squaring / sparse multiplication /
+//     cyclotomic squaring, line evaluations next to the accumulator update).  microcode/sched.py pairs them at
+//     build time; lane l < 16 of a warp runs unit A's instruction of pairing l, lane l + 16 unit B's, on the same
+//     slots.  Same shared memory per pairing, twice the warps (16 per SM at <= 128 registers), the lean
+//     per-lane instruction stream of the thread-per-pairing form.
+// The units of a bundle differ only in operand fields, masks and selects - never in control flow.  Every store
+// sits behind a warp barrier: both units have read their operands before either writes (a destination may
+// reuse the slot of a source that dies in the bundle).
 #pragma once
 #include "fp2.cuh"
 #include "microcode_ops.h"
@@ -25,45 +35,46 @@
 #define BNP_NARR 6
 #define BNP_MAX_CONST 128
 #define BNP_MAX_PHASES 16
-#define BNP_CHUNK 32  // pairings per warp-task
+#define BNP_CHUNK 16  // pairings per warp-task (two lanes each)
 
 struct VmArgs {
-    const u64* prog[BNP_MAX_PHASES];  // instruction words of each phase (device global memory)
+    const u64* prog[BNP_MAX_PHASES];  // bundles of each phase (device global memory, 16-byte aligned)
     u64* arr[BNP_NARR];     // SoA arrays: [K][4][stride] u64 (ids in microcode/isa.py); arr[5] = phase state
-    uint4* scratch;         // [n_scratch][4][total_threads] uint4
+    uint4* scratch;         // [n_scratch][4][resident pairings] uint4
     u32 n;                  // elements to process
     u32 stride;             // elements per limb row of the arrays (>= n)
-    u32* counter;           // work counter (zeroed before launch): warps claim (phase, 32-element chunk) tasks
+    u32* counter;           // work counter (zeroed before launch): warps claim (phase, 16-element chunk) tasks
     u32* progress;          // per chunk: number of completed phases (zeroed before launch; unused when n_phases == 1)
     u32 n_phases;
 };
 
 __device__ __constant__ u32 BNP_CONSTS[BNP_MAX_CONST][16];
 
-// Shared-memory slots: [slot][quad][thread] uint4; quads 0,1 = c0, quads 2,3 = c1.
+// Shared-memory slots: [slot][quad][pairing] uint4; quads 0,1 = c0, quads 2,3 = c1.  P = pairings per block.
 template <int T>
 struct Slots {
-    uint4* base;  // already offset by threadIdx.x
+    static constexpr int P = T / 2;
+    uint4* base;  // already offset by the pairing's index in the block
     __device__ __forceinline__ void load_half(u32* r, u32 s, u32 half) const {
-        const uint4* p = base + s * (4 * T) + half * (2 * T);
-        uint4 q0 = p[0], q1 = p[T];
+        const uint4* p = base + s * (4 * P) + half * (2 * P);
+        uint4 q0 = p[0], q1 = p[P];
         r[0] = q0.x; r[1] = q0.y; r[2] = q0.z; r[3] = q0.w;
         r[4] = q1.x; r[5] = q1.y; r[6] = q1.z; r[7] = q1.w;
     }
     __device__ __forceinline__ void load(Fp2& r, u32 s) const {
-        const uint4* p = base + s * (4 * T);
-        uint4 q0 = p[0], q1 = p[T], q2 = p[2 * T], q3 = p[3 * T];
+        const uint4* p = base + s * (4 * P);
+        uint4 q0 = p[0], q1 = p[P], q2 = p[2 * P], q3 = p[3 * P];
         r.c0[0] = q0.x; r.c0[1] = q0.y; r.c0[2] = q0.z; r.c0[3] = q0.w;
         r.c0[4] = q1.x; r.c0[5] = q1.y; r.c0[6] = q1.z; r.c0[7] = q1.w;
         r.c1[0] = q2.x; r.c1[1] = q2.y; r.c1[2] = q2.z; r.c1[3] = q2.w;
         r.c1[4] = q3.x; r.c1[5] = q3.y; r.c1[6] = q3.z; r.c1[7] = q3.w;
     }
     __device__ __forceinline__ void store(u32 s, const Fp2& r) const {
-        uint4* p = base + s * (4 * T);
+        uint4* p = base + s * (4 * P);
         p[0] = make_uint4(r.c0[0], r.c0[1], r.c0[2], r.c0[3]);
-        p[T] = make_uint4(r.c0[4], r.c0[5], r.c0[6], r.c0[7]);
-        p[2 * T] = make_uint4(r.c1[0], r.c1[1], r.c1[2], r.c1[3]);
-        p[3 * T] = make_uint4(r.c1[4], r.c1[5], r.c1[6], r.c1[7]);
+        p[P] = make_uint4(r.c0[4], r.c0[5], r.c0[6], r.c0[7]);
+        p[2 * P] = make_uint4(r.c1[0], r.c1[1], r.c1[2], r.c1[3]);
+        p[3 * P] = make_uint4(r.c1[4], r.c1[5], r.c1[6], r.c1[7]);
     }
 };
 
@@ -84,45 +95,40 @@ __device__ __forceinline__ void stg_fp(u64* arr, u32 f, u32 n, u32 e, const u32*
     for (int j = 0; j < 4; j++) p[(size_t)j * n] = (u64)r[2 * j] | ((u64)r[2 * j + 1] << 32);
 }
 
+// r = sel ? a : b, limb-wise (sel is per lane: never a branch)
+__device__ __forceinline__ void sel8(u32* r, bool sel, const u32* a, const u32* b) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = sel ? a[i] : b[i];
+}
+
+// What a unit adds for an optional, optionally negated canonical operand t:
+//     t (present, positive)   p - t (present, negated)   0 (absent)
+// any_neg / all_neg / any_absent describe the BUNDLE and are warp-uniform; my_* are this unit's own bits.  When the
+// two units agree (the common case: the tower formulas are symmetric) there is no select and no mask.
+__device__ __forceinline__ void prep_addend(u32* t, bool my_pres, bool my_neg, bool any_neg, bool all_neg, bool any_absent) {
+    if (any_neg) {
+        u32 nt[8];
+        fp_p_minus(nt, t);
+        if (all_neg) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) t[i] = nt[i];
+        } else {
+            sel8(t, my_neg, nt, t);
+        }
+    }
+    if (any_absent) {
+        const u32 m = my_pres ? 0xffffffffu : 0u;
+#pragma unroll
+        for (int i = 0; i < 8; i++) t[i] &= m;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // LIN engine:  out_c = sum_j mult_j * (neg_j ? p - z_j : z_j)  <  1024 p  for c = 0, 1, each reduced once by a
 // quotient estimate.  An entry is one pair of 4-deep IMAD.WIDE chains into 64-bit-column accumulators (E: even limb
-// positions, O: odd).  Entries are 16 bits, [slot:8][half:1][neg:1][mult:6], and come in (component 0, component 1)
-// pairs, one pair per 32-bit word; the two components are independent chains the scheduler interleaves.  A pair is
-// fetched one iteration ahead of its use (the loop is software-pipelined by hand); multiplier 0 pads the shorter
-// list.  Every test below is warp-uniform.
+// positions, O: odd).  Entries are 16 bits, [slot:8][half:1][neg:1][mult:6]; one 64-bit word per entry index holds
+// unit A's (c0, c1) pair in its low half and unit B's in its high half.  Multiplier 0 pads the shorter lists.
 // ---------------------------------------------------------------------------------------------
-#define BNP_LIN_FETCH(J, ZA, ZB, TT)                                          \
-    {                                                                         \
-        TT = __ldg(ents + (J));                                               \
-        S.load_half(ZA, TT & 0xffu, (TT >> 8) & 1u);                          \
-        S.load_half(ZB, (TT >> 16) & 0xffu, (TT >> 24) & 1u);                 \
-    }
-#define BNP_LIN_ACC(ZA, ZB, TT)                                               \
-    {                                                                         \
-        if (TT & 0x00000200u) fp_p_minus(ZA, ZA);                             \
-        if (TT & 0x02000000u) fp_p_minus(ZB, ZB);                             \
-        const u32 ma_ = (TT >> 10) & 63u, mb_ = TT >> 26;                     \
-        chain_acc64(E0, ma_, ZA[0], ZA[2], ZA[4], ZA[6]);                     \
-        chain_acc64(O0, ma_, ZA[1], ZA[3], ZA[5], ZA[7]);                     \
-        chain_acc64(E1, mb_, ZB[0], ZB[2], ZB[4], ZB[6]);                     \
-        chain_acc64(O1, mb_, ZB[1], ZB[3], ZB[5], ZB[7]);                     \
-    }
-// first pair of a LIN: the accumulators are written, not accumulated into (no zero-initialisation)
-#define BNP_LIN_ACC_FIRST(ZA, ZB, TT)                                         \
-    {                                                                         \
-        if (TT & 0x00000200u) fp_p_minus(ZA, ZA);                             \
-        if (TT & 0x02000000u) fp_p_minus(ZB, ZB);                             \
-        const u32 ma_ = (TT >> 10) & 63u, mb_ = TT >> 26;                     \
-        _Pragma("unroll") for (int c_ = 0; c_ < 4; c_++) {                    \
-            E0[c_] = (u64)ma_ * ZA[2 * c_];                                   \
-            O0[c_] = (u64)ma_ * ZA[2 * c_ + 1];                               \
-            E1[c_] = (u64)mb_ * ZB[2 * c_];                                   \
-            O1[c_] = (u64)mb_ * ZB[2 * c_ + 1];                               \
-        }                                                                     \
-        E0[4] = O0[4] = E1[4] = O1[4] = 0ull;                                 \
-    }
-
 // v = E + (O << 32): nine limbs (the total is below 2^264, so limb 9 of either part is zero)
 __device__ __forceinline__ void lin_merge(u32* v, const u64* Ec, const u64* Oc) {
     u32 E[10], O[10];   // E, O: 64-bit columns at even / odd limb positions
@@ -148,33 +154,27 @@ __device__ __forceinline__ void lin_merge(u32* v, const u64* Ec, const u64* Oc) 
 }
 
 template <int T>
-__device__ __forceinline__ void vm_lin(const Slots<T>& S, Fp2& out, u32 n, const u64* more) {
-    const u32* ents = (const u32*)more;  // pair j is the j-th 32-bit word of the entry list
+__device__ __forceinline__ void vm_lin(const Slots<T>& S, u32 unit, Fp2& out, u32 n, const u64* ents) {
     u64 E0[5], O0[5], E1[5], O1[5];
-#ifdef BNP_LIN_PIPELINED
-    // hand-pipelined form (three copies of the entry body: +3 KB of hot code)
-    u32 za[8], zb[8], ya[8], yb[8], ta, ua;
-    BNP_LIN_FETCH(0u, za, zb, ta);
-    if (1u < n) BNP_LIN_FETCH(1u, ya, yb, ua);
-    BNP_LIN_ACC_FIRST(za, zb, ta);
-#pragma unroll 1
-    for (u32 j = 1; j < n; j += 2u) {   // (ya, yb) hold pair j
-        if (j + 1u < n) BNP_LIN_FETCH(j + 1u, za, zb, ta);
-        BNP_LIN_ACC(ya, yb, ua);
-        if (j + 1u >= n) break;
-        if (j + 2u < n) BNP_LIN_FETCH(j + 2u, ya, yb, ua);
-        BNP_LIN_ACC(za, zb, ta);
-    }
-#else
 #pragma unroll
     for (int i = 0; i < 5; i++) E0[i] = O0[i] = E1[i] = O1[i] = 0ull;
 #pragma unroll 1
     for (u32 j = 0; j < n; j++) {
-        u32 za[8], zb[8], ta;
-        BNP_LIN_FETCH(j, za, zb, ta);
-        BNP_LIN_ACC(za, zb, ta);
+        const u64 w = __ldg(ents + j);
+        const u32 lo = (u32)w, hi = (u32)(w >> 32);
+        const u32 t = unit ? hi : lo;
+        const u32 any = lo | hi, all = lo & hi;
+        u32 za[8], zb[8];
+        S.load_half(za, t & 0xffu, (t >> 8) & 1u);
+        S.load_half(zb, (t >> 16) & 0xffu, (t >> 24) & 1u);
+        prep_addend(za, true, (t & 0x00000200u) != 0u, (any & 0x00000200u) != 0u, (all & 0x00000200u) != 0u, false);
+        prep_addend(zb, true, (t & 0x02000000u) != 0u, (any & 0x02000000u) != 0u, (all & 0x02000000u) != 0u, false);
+        const u32 ma = (t >> 10) & 63u, mb = t >> 26;
+        chain_acc64(E0, ma, za[0], za[2], za[4], za[6]);
+        chain_acc64(O0, ma, za[1], za[3], za[5], za[7]);
+        chain_acc64(E1, mb, zb[0], zb[2], zb[4], zb[6]);
+        chain_acc64(O1, mb, zb[1], zb[3], zb[5], zb[7]);
     }
-#endif
     u32 v0[9], v1[9];
     lin_merge(v0, E0, O0);
     lin_merge(v1, E1, O1);
@@ -183,16 +183,23 @@ __device__ __forceinline__ void vm_lin(const Slots<T>& S, Fp2& out, u32 n, const
 }
 
 // ---------------------------------------------------------------------------------------------
-// Product class (MUL / SQR / MULFP), one shared tail:
+// Product class (MUL / SQR / MULFP), one shared body:
 //   (T0, T1) = the two wide components;  T += 2^256 * hi terms;  r' = canon(redc(T));  [S[d] = r'];  [S[d2] = LIN(r', ...)]
-// On entry `pc` points at the word after the instruction; on exit `ins` holds the next instruction
-// and `pc` points past it.
+// `pc` points at the bundle; returns the address of the next bundle.
 // ---------------------------------------------------------------------------------------------
 template <int T>
-__device__ __forceinline__ void vm_product(const Slots<T>& S, u32 op, const u64*& pc, u64& ins, u32 d, u32 a, u32 b, u32 c,
-                                           u32 ee, u32 imm) {
-    const u64* p0 = pc;
-    const u64 w0 = __ldg(p0), w1 = __ldg(p0 + 1);  // extension word (or the next instruction), the word after it
+__device__ __forceinline__ const u64* vm_product(const Slots<T>& S, u32 unit, bool act, u32 op, const u64* pc, u64 wA, u64 wB,
+                                                 u64 mine) {
+    const u32 lo = (u32)mine, hi = (u32)(mine >> 32);
+    const u32 d = (lo >> 8) & 0xffu, a = (lo >> 16) & 0xffu, b = lo >> 24;
+    const u32 c = hi & 0xffu, ee = (hi >> 8) & 0xffu, imm = hi >> 16;
+    const u32 immA = (u32)(wA >> 48), immB = (u32)(wB >> 48);
+    const u32 any = immA | immB, all = immA & immB;
+    u64 xA = 0, xB = 0;
+    if (any & BNP_MUL_EXT) {  // extension words of the two units
+        xA = __ldg(pc + 2);
+        xB = __ldg(pc + 3);
+    }
     // Every product-class opcode starts with the same TWO independent wide products A = u0 * v0, B = u1 * v1
     // (one copy of that code in the instruction stream: the hot path has to stay inside the 32 KB L1.5):
     //   MUL:    A = x0 y0, B = x1 y1, then C = (x0 + x1)(y0 + y1);  T0 = A - B (+ p 2^256 if negative), T1 = C - A - B
@@ -204,20 +211,30 @@ __device__ __forceinline__ void vm_product(const Slots<T>& S, u32 op, const u64*
         Fp2 x, y;
         S.load(x, a);
         S.load(y, c);
-        if (imm & (BNP_MUL_B | BNP_MUL_E)) {  // Karatsuba-level operands: (a +- b) * (c +- e), sums kept lazy (< 2p)
+        // Karatsuba-level operands: (a +- b) * (c +- e), sums kept lazy (< 2p); a - b is computed as a + (p - b)
+        if (any & BNP_MUL_B) {
             Fp2 t;
-            if (imm & BNP_MUL_B) {
-                S.load(t, b);
-                if (imm & BNP_MUL_BNEG) fp2_sub_lazy(x, x, t); else fp2_add_lazy(x, x, t);
-                if (imm & BNP_MUL_BCANON) {
-                    fp_cond_sub_p(x.c0);
-                    fp_cond_sub_p(x.c1);
-                }
+            S.load(t, b);
+            const bool pres = (imm & BNP_MUL_B) != 0u, neg = (imm & BNP_MUL_BNEG) != 0u;
+            const bool any_neg = (any & BNP_MUL_BNEG) != 0u, all_neg = (all & BNP_MUL_BNEG) != 0u, any_abs = !(all & BNP_MUL_B);
+            prep_addend(t.c0, pres, neg, any_neg, all_neg, any_abs);
+            prep_addend(t.c1, pres, neg, any_neg, all_neg, any_abs);
+            add8(x.c0, x.c0, t.c0);
+            add8(x.c1, x.c1, t.c1);
+            if (any & BNP_MUL_BCANON) {
+                fp_cond_sub_p(x.c0);
+                fp_cond_sub_p(x.c1);
             }
-            if (imm & BNP_MUL_E) {
-                S.load(t, ee);
-                if (imm & BNP_MUL_ENEG) fp2_sub_lazy(y, y, t); else fp2_add_lazy(y, y, t);
-            }
+        }
+        if (any & BNP_MUL_E) {
+            Fp2 t;
+            S.load(t, ee);
+            const bool pres = (imm & BNP_MUL_E) != 0u, neg = (imm & BNP_MUL_ENEG) != 0u;
+            const bool any_neg = (any & BNP_MUL_ENEG) != 0u, all_neg = (all & BNP_MUL_ENEG) != 0u, any_abs = !(all & BNP_MUL_E);
+            prep_addend(t.c0, pres, neg, any_neg, all_neg, any_abs);
+            prep_addend(t.c1, pres, neg, any_neg, all_neg, any_abs);
+            add8(y.c0, y.c0, t.c0);
+            add8(y.c1, y.c1, t.c1);
         }
         add8(sx, x.c0, x.c1);  // < 4p < 2^256
         add8(sy, y.c0, y.c1);
@@ -226,10 +243,17 @@ __device__ __forceinline__ void vm_product(const Slots<T>& S, u32 op, const u64*
     } else if (op == BNP_OP_SQR) {
         Fp2 x;
         S.load(x, a);
-        if (imm & BNP_MUL_B) {
+        if (any & BNP_MUL_B) {  // (a +- b)^2, the sum made canonical
             Fp2 t;
             S.load(t, b);
-            if (imm & BNP_MUL_BNEG) fp2_sub(x, x, t); else fp2_add(x, x, t);
+            const bool pres = (imm & BNP_MUL_B) != 0u, neg = (imm & BNP_MUL_BNEG) != 0u;
+            const bool any_neg = (any & BNP_MUL_BNEG) != 0u, all_neg = (all & BNP_MUL_BNEG) != 0u, any_abs = !(all & BNP_MUL_B);
+            prep_addend(t.c0, pres, neg, any_neg, all_neg, any_abs);
+            prep_addend(t.c1, pres, neg, any_neg, all_neg, any_abs);
+            add8(x.c0, x.c0, t.c0);
+            add8(x.c1, x.c1, t.c1);
+            fp_cond_sub_p(x.c0);
+            fp_cond_sub_p(x.c1);
         }
         add8(u0, x.c0, x.c1);
         fp_sub(v0, x.c0, x.c1);
@@ -255,23 +279,23 @@ __device__ __forceinline__ void vm_product(const Slots<T>& S, u32 op, const u64*
 #pragma unroll
         for (int i = 0; i < 16; i++) T1[i] = P2[i];
     }
-    u32 np = 0, d2 = 0;  // np: entry pairs of the post LIN
-    bool store_r = true;
-    if (imm & BNP_MUL_EXT) {
-        const u32 xl = (u32)w0, xh = (u32)(w0 >> 32);
-        d2 = xl & 0xffu;
-        const u32 hflags = xh & 0xffu;
+    const u64 xm = unit ? xB : xA;
+    const u32 xl = (u32)xm, xh = (u32)(xm >> 32);
+    u32 np = 0;
+    if (any & BNP_MUL_EXT) {
+        const u32 hfA = (u32)(xA >> 32), hfB = (u32)(xB >> 32);   // hflags in bits 0-7, present mask in bits 16-23
+        const u32 hany = hfA | hfB, hall = hfA & hfB;
         np = (xh >> 8) & 0xffu;
-        store_r = np == 0u || (hflags & BNP_EXT_STORE_R);
-        const u32 n_hi = hflags & 3u;
+        const u32 n_hi = xh & 3u;
 #pragma unroll 1
         for (u32 i = 0; i < n_hi; i++) {
             Fp2 h;
             S.load(h, (xl >> (8u * (i + 1u))) & 0xffu);
-            if (hflags & (4u << i)) {
-                fp_p_minus(h.c0, h.c0);
-                fp_p_minus(h.c1, h.c1);
-            }
+            const bool pres = ((xh >> (16u + i)) & 1u) != 0u, neg = ((xh >> (2u + i)) & 1u) != 0u;
+            const bool any_neg = ((hany >> (2u + i)) & 1u) != 0u, all_neg = ((hall >> (2u + i)) & 1u) != 0u;
+            const bool any_abs = ((hall >> (16u + i)) & 1u) == 0u;
+            prep_addend(h.c0, pres, neg, any_neg, all_neg, any_abs);
+            prep_addend(h.c1, pres, neg, any_neg, all_neg, any_abs);
             wide_add_hi(T0, h.c0);
             wide_add_hi(T1, h.c1);
         }
@@ -279,52 +303,49 @@ __device__ __forceinline__ void vm_product(const Slots<T>& S, u32 op, const u64*
     Fp2 r;
     fp_redc_lazy(r.c0, T0);
     fp_redc_lazy(r.c1, T1);
-    fp_canon(r.c0, (imm >> BNP_MUL_CANON_SHIFT) & 3u);
-    fp_canon(r.c1, (imm >> (BNP_MUL_CANON_SHIFT + 2)) & 3u);
-    if (!(imm & BNP_MUL_EXT)) {
-        S.store(d, r);
-        ins = w0;
-        pc = p0 + 1;
-        return;
+    fp_canon(r.c0, (immA >> BNP_MUL_CANON_SHIFT) & 3u);
+    fp_canon(r.c1, (immA >> (BNP_MUL_CANON_SHIFT + 2)) & 3u);
+    __syncwarp();  // both units have read their operands (a destination may alias a source slot of either unit)
+    if (!(any & BNP_MUL_EXT)) {
+        if (act) S.store(d, r);
+        return pc + 2;
     }
+    const u32 d2 = xl & 0xffu;
+    const u32 np_own = xh >> 24;
+    const bool store_r = np_own == 0u || (xh & BNP_EXT_STORE_R);
+    const u64* next = pc + 4 + np + (np & 1u);
     if (np) {
         // Post stage: park r' where the entries expect it, then run the LIN engine on the entry list.
-        const u32 nw = (np + 1u) >> 1;
-        const u64 nx = __ldg(p0 + 1 + nw);
-        S.store(store_r ? d : d2, r);
+        if (act) S.store(store_r ? d : d2, r);
+        __syncwarp();
         Fp2 o;
-        vm_lin<T>(S, o, np, p0 + 1);
-        S.store(d2, o);
-        ins = nx;
-        pc = p0 + 2 + nw;
-        return;
+        vm_lin<T>(S, unit, o, np, pc + 4);
+        __syncwarp();
+        if (act && np_own) S.store(d2, o);
+        return next;
     }
-    S.store(d, r);
-    ins = w1;
-    pc = p0 + 2;
+    if (act) S.store(d, r);
+    return next;
 }
 
 #ifndef BNP_MINB
-// Resident blocks of 64 threads per SM the register allocation must allow.  Measured (profiles/slots_sweep_r2_solo.txt):
-// 6 blocks = 12 warps per SM with 9 slots per pairing beats 4 blocks = 8 warps with 14 slots by 4.6 % although the
-// smaller slot file costs three times the spill traffic and 1500 stand-alone linear instructions - a third warp per
-// scheduler covers more of the carry-chain latency than the spills cost.  12 warps: up to 170 registers.
-#define BNP_MINB 6
+#define BNP_MINB 8  // resident blocks of 64 threads per SM the register allocation must allow (16 warps: <= 128 registers)
 #endif
 
 template <int T>
 __global__ void __launch_bounds__(T, (BNP_MINB * 64) / T) bnp_vm_kernel(VmArgs args) {
     extern __shared__ uint4 bnp_smem[];
     const u32 lane = threadIdx.x & 31u;
+    const u32 unit = lane >> 4;
+    const u32 pib = (threadIdx.x >> 5) * BNP_CHUNK + (lane & 15u);  // this pairing's index in the block
     Slots<T> S;
-    S.base = bnp_smem + threadIdx.x;
-    const u32 total = gridDim.x * T;
-    const u32 gtid = blockIdx.x * T + threadIdx.x;
-    uint4* scr = args.scratch + gtid;
+    S.base = bnp_smem + pib;
+    const u32 totalp = gridDim.x * (T / 2);
+    uint4* scr = args.scratch + (blockIdx.x * (T / 2) + pib);
     const u32 n = args.n, stride = args.stride;
 
     // Persistent warps: each claims the next task when it finishes one.  A task is one phase of the program over one
-    // chunk of 32 elements, handed out breadth-first (every chunk's phase 0, then every chunk's phase 1, ...), so
+    // chunk of 16 elements, handed out breadth-first (every chunk's phase 0, then every chunk's phase 1, ...), so
     // that only the last phase of a batch runs on a partly filled machine.  Phase p of a chunk waits for phase p-1
     // of the same chunk, which was claimed earlier by a warp that never waits on anything later - so the wait cannot
     // deadlock and is almost never taken.
@@ -348,34 +369,36 @@ __global__ void __launch_bounds__(T, (BNP_MINB * 64) / T) bnp_vm_kernel(VmArgs a
             }
             __syncwarp();
         }
-        const u32 e_raw = chunk * BNP_CHUNK + lane;
+        const u32 e_raw = chunk * BNP_CHUNK + (lane & 15u);
         const bool active = e_raw < n;
-        const u32 e = active ? e_raw : n - 1;  // idle lanes shadow the last element and never store
+        const u32 e = active ? e_raw : n - 1;  // idle pairings shadow the last element and never store
         const u64* pc = args.prog[0];
 #pragma unroll
         for (int k = 1; k < BNP_MAX_PHASES; k++)
             if (phase == (u32)k) pc = args.prog[k];
-        u64 ins = __ldg(pc++);
         for (;;) {
-            const u32 lo = (u32)ins, hi = (u32)(ins >> 32);
-            const u32 op = lo & 0xffu, d = (lo >> 8) & 0xffu, a = (lo >> 16) & 0xffu, b = lo >> 24;
-            const u32 c = hi & 0xffu, ee = (hi >> 8) & 0xffu, imm = hi >> 16;
+            const u64 wA = __ldg(pc), wB = __ldg(pc + 1);
+            const u32 op = (u32)wA & 0xffu;
             if (op == BNP_OP_END) break;
+            const bool act = !(unit && ((u32)wB & 0x80u));  // an idle unit B shadows unit A and stores nothing
+            const u64 mine = unit ? wB : wA;
+            __syncwarp();  // the previous bundle's stores are visible to the partner unit
             if (op == BNP_OP_MUL || op == BNP_OP_SQR || op == BNP_OP_MULFP) {
-                vm_product<T>(S, op, pc, ins, d, a, b, c, ee, imm);
+                pc = vm_product<T>(S, unit, act, op, pc, wA, wB, mine);
                 continue;
             }
-            if (op == BNP_OP_LIN) {  // d = LIN(slots), a = number of entry pairs
-                const u32 nw = (a + 1u) >> 1;
-                const u64 nx = __ldg(pc + nw);
+            const u32 lo = (u32)mine, hi = (u32)(mine >> 32);
+            const u32 d = (lo >> 8) & 0xffu, a = (lo >> 16) & 0xffu, b = lo >> 24;
+            const u32 imm = hi >> 16;
+            if (op == BNP_OP_LIN) {  // d = LIN(slots), a = number of entry words
                 Fp2 o;
-                vm_lin<T>(S, o, a, pc);
-                S.store(d, o);
-                ins = nx;
-                pc += nw + 1;
+                vm_lin<T>(S, unit, o, a, pc + 2);
+                __syncwarp();
+                if (act) S.store(d, o);
+                pc += 2 + a + (a & 1u);
                 continue;
             }
-            const u64 nxt = __ldg(pc++);  // prefetch (every program ends with END followed by padding)
+            pc += 2;
             Fp2 x, y, r;
             switch (op) {
                 case BNP_OP_LDC:
@@ -384,82 +407,92 @@ __global__ void __launch_bounds__(T, (BNP_MINB * 64) / T) bnp_vm_kernel(VmArgs a
                         r.c0[i] = BNP_CONSTS[imm][i];
                         r.c1[i] = BNP_CONSTS[imm][8 + i];
                     }
-                    S.store(d, r);
+                    if (act) S.store(d, r);
                     break;
                 case BNP_OP_LDG:
                     ldg_fp(r.c0, args.arr[imm], a, stride, e);
                     ldg_fp(r.c1, args.arr[imm], b, stride, e);
-                    S.store(d, r);
+                    if (act) S.store(d, r);
                     break;
                 case BNP_OP_STG:
                     S.load(x, a);
-                    if (active) {
+                    if (act && active) {
                         stg_fp(args.arr[imm], d, stride, e, x.c0);
                         stg_fp(args.arr[imm], b, stride, e, x.c1);
                     }
                     break;
                 case BNP_OP_SPILL: {
-                    const uint4* p = S.base + a * (4 * T);
-                    uint4* q = scr + (size_t)imm * 4 * total;
-                    q[0] = p[0];
-                    q[total] = p[T];
-                    q[2 * (size_t)total] = p[2 * T];
-                    q[3 * (size_t)total] = p[3 * T];
+                    const uint4* p = S.base + a * (4 * Slots<T>::P);
+                    uint4* q = scr + (size_t)imm * 4 * totalp;
+                    if (act) {
+                        q[0] = p[0];
+                        q[totalp] = p[Slots<T>::P];
+                        q[2 * (size_t)totalp] = p[2 * Slots<T>::P];
+                        q[3 * (size_t)totalp] = p[3 * Slots<T>::P];
+                    }
                     break;
                 }
                 case BNP_OP_FILL: {
-                    uint4* p = S.base + d * (4 * T);
-                    const uint4* q = scr + (size_t)imm * 4 * total;
+                    uint4* p = S.base + d * (4 * Slots<T>::P);
+                    const uint4* q = scr + (size_t)imm * 4 * totalp;
                     // read-once data: bypass L1 (what little L1 the slots leave holds the instruction words)
-                    const uint4 q0 = __ldcg(q), q1 = __ldcg(q + total), q2 = __ldcg(q + 2 * (size_t)total),
-                                q3 = __ldcg(q + 3 * (size_t)total);
-                    p[0] = q0;
-                    p[T] = q1;
-                    p[2 * T] = q2;
-                    p[3 * T] = q3;
+                    const uint4 q0 = __ldcg(q), q1 = __ldcg(q + totalp), q2 = __ldcg(q + 2 * (size_t)totalp),
+                                q3 = __ldcg(q + 3 * (size_t)totalp);
+                    if (act) {
+                        p[0] = q0;
+                        p[Slots<T>::P] = q1;
+                        p[2 * Slots<T>::P] = q2;
+                        p[3 * Slots<T>::P] = q3;
+                    }
                     break;
                 }
-                case BNP_OP_INV:  // once or twice per program
+                case BNP_OP_INV:  // once or twice per program, always alone in its bundle: unit B shadows unit A
                     S.load(x, a);
                     fp2_inv(r, x);
-                    S.store(d, r);
+                    __syncwarp();
+                    if (act) S.store(d, r);
                     break;
                 case BNP_OP_ADD:
                     S.load(x, a);
                     S.load(y, b);
                     fp2_add(r, x, y);
-                    S.store(d, r);
+                    __syncwarp();
+                    if (act) S.store(d, r);
                     break;
                 case BNP_OP_SUB:
                     S.load(x, a);
                     S.load(y, b);
                     fp2_sub(r, x, y);
-                    S.store(d, r);
+                    __syncwarp();
+                    if (act) S.store(d, r);
                     break;
                 case BNP_OP_DBL:
                     S.load(x, a);
                     fp2_add(r, x, x);
-                    S.store(d, r);
+                    __syncwarp();
+                    if (act) S.store(d, r);
                     break;
                 case BNP_OP_NEG:
                     S.load(x, a);
                     fp2_neg(r, x);
-                    S.store(d, r);
+                    __syncwarp();
+                    if (act) S.store(d, r);
                     break;
                 case BNP_OP_CONJ:
                     S.load(x, a);
                     fp2_conj(r, x);
-                    S.store(d, r);
+                    __syncwarp();
+                    if (act) S.store(d, r);
                     break;
                 case BNP_OP_MULXI:
                     S.load(x, a);
                     fp2_mul_xi(r, x);
-                    S.store(d, r);
+                    __syncwarp();
+                    if (act) S.store(d, r);
                     break;
                 default:
                     break;
             }
-            ins = nxt;
         }
         if (args.n_phases > 1u) {  // publish: this chunk's state is complete up to and including `phase`
             __threadfence();
@@ -467,6 +500,7 @@ __global__ void __launch_bounds__(T, (BNP_MINB * 64) / T) bnp_vm_kernel(VmArgs a
             if (lane == 0)
                 asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(args.progress + chunk), "r"(phase + 1u) : "memory");
         }
+        __syncwarp();  // slots are reused by the next task
     }
 }
 

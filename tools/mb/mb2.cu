@@ -102,6 +102,25 @@ __global__ void __launch_bounds__(T, MINB) vmk(Args args) {
                 fp_canon(r.c0, op == 5u ? 1u : 0u);
                 fp_canon(r.c1, op == 5u ? 1u : 0u);
                 S.store(d, r);
+            } else if (op == 6u) {   // two independent MULs in one instruction: d = a*c, d+1 = b*e
+                Fp2 x2, y2, r2;
+                S.load(x, a);
+                S.load(y, c);
+                S.load(x2, b);
+                S.load(y2, ee);
+                u32 T0[16], T1[16], U0[16], U1[16];
+                fp2_mul_wide(T0, T1, x, y);
+                fp2_mul_wide(U0, U1, x2, y2);
+                fp_redc_lazy(r.c0, T0);
+                fp_redc_lazy(r.c1, T1);
+                fp_redc_lazy(r2.c0, U0);
+                fp_redc_lazy(r2.c1, U1);
+                fp_canon(r.c0, 0u);
+                fp_canon(r.c1, 0u);
+                fp_canon(r2.c0, 0u);
+                fp_canon(r2.c1, 0u);
+                S.store(d, r);
+                S.store(d == NS - 1 ? 0 : d + 1, r2);
             } else if (op == 2u) {
                 S.load(x, a);
                 u32 T0[16], T1[16];
@@ -134,7 +153,7 @@ static std::vector<u64> make_prog(int kind, int ns, int n) {
     auto rnd = [&]() { st = st * 1664525u + 1013904223u; return st >> 8; };
     for (int i = 0; i < n; i++) {
         u32 op;
-        if (kind == 0) op = 1; else if (kind == 1) op = 2; else if (kind == 2) op = 3; else if (kind == 3) op = 4; else if (kind == 4) op = 5;
+        if (kind == 0) op = 1; else if (kind == 1) op = 2; else if (kind == 2) op = 3; else if (kind == 3) op = 4; else if (kind == 4) op = 5; else if (kind == 6) op = 6;
         else { u32 r = rnd() % 100; op = r < 52 ? 1 : r < 79 ? 2 : 3; }   // program-like mix: 4038 MUL, 2091 SQR, ~1600 linear
         u32 d = i % ns, a = rnd() % ns, b = rnd() % ns, c = rnd() % ns, e = rnd() % ns;
         w.push_back((u64)op | ((u64)d << 8) | ((u64)a << 16) | ((u64)b << 24) | ((u64)c << 32) | ((u64)e << 40));
@@ -145,8 +164,8 @@ static std::vector<u64> make_prog(int kind, int ns, int n) {
 
 template <int T, int MINB, int NS>
 static void run_cfg(const char* cfg) {
-    const char* names[] = {"mul", "sqr", "add", "mul_il", "mul_pre", "mix"};
-    const double macs[] = {336, 272, 0, 336, 336, 0.52 * 336 + 0.27 * 272};
+    const char* names[] = {"mul", "sqr", "add", "mul_il", "mul_pre", "mix", "mul2"};
+    const double macs[] = {336, 272, 0, 336, 336, 0.52 * 336 + 0.27 * 272, 672};
     cudaFuncSetAttribute(vmk<T, MINB, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, NS * 64 * T);
     int nb = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, vmk<T, MINB, NS>, T, NS * 64 * T);
@@ -157,7 +176,7 @@ static void run_cfg(const char* cfg) {
     cudaMalloc(&out, 1 << 24);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int kind = 0; kind < 6; kind++) {
+    for (int kind = 0; kind < 7; kind++) {
         const int nins = 2048, reps = 4;
         std::vector<u64> w = make_prog(kind, NS, nins);
         u64* dp;
@@ -189,7 +208,5 @@ static void run_cfg(const char* cfg) {
 int main() {
     run_cfg<64, 4, 14>("8 warps/SM");
     run_cfg<64, 6, 9>("12 warps/SM");
-    run_cfg<64, 8, 7>("16 warps/SM");
-    run_cfg<32, 8, 14>("8 warps/SM, 32-thread blocks");
     return 0;
 }
