@@ -41,6 +41,10 @@ struct VmArgs {
 __device__ __constant__ u32 BNP_CONSTS[BNP_MAX_CONST][16];
 
 // Shared-memory slots: [slot][quad][thread] uint4; quads 0,1 = c0, quads 2,3 = c1.
+// (Measured and dropped in round 2: "memory operands" - slot fields that name a scratch entry in global memory, so
+// that a value read once is not FILLed into a slot first.  The programs shrank from 18.4 k to 12.9 k instructions per
+// pairing, but a second access path at every operand site - by a uniform branch or by generic addressing - cost the
+// kernel 10 % before a single memory operand was used: 2.15-2.20 M pairings/s against 2.40 M.)
 template <int T>
 struct Slots {
     uint4* base;  // already offset by threadIdx.x
@@ -189,10 +193,10 @@ __device__ __forceinline__ void vm_lin(const Slots<T>& S, Fp2& out, u32 n, const
 // and `pc` points past it.
 // ---------------------------------------------------------------------------------------------
 template <int T>
-__device__ __forceinline__ void vm_product(const Slots<T>& S, u32 op, const u64*& pc, u64& ins, u32 d, u32 a, u32 b, u32 c,
-                                           u32 ee, u32 imm) {
+__device__ __forceinline__ void vm_product(const Slots<T>& S, u32 op, const u64*& pc, u64& ins, const u64 w0, u32 d, u32 a,
+                                           u32 b, u32 c, u32 ee, u32 imm) {
     const u64* p0 = pc;
-    const u64 w0 = __ldg(p0), w1 = __ldg(p0 + 1);  // extension word (or the next instruction), the word after it
+    const u64 w1 = __ldg(p0 + 1);  // w0: extension word (or the next instruction), w1: the word after it
     // Every product-class opcode starts with the same TWO independent wide products A = u0 * v0, B = u1 * v1
     // (one copy of that code in the instruction stream: the hot path has to stay inside the 32 KB L1.5):
     //   MUL:    A = x0 y0, B = x1 y1, then C = (x0 + x1)(y0 + y1);  T0 = A - B (+ p 2^256 if negative), T1 = C - A - B
@@ -356,28 +360,35 @@ __global__ void __launch_bounds__(T, (BNP_MINB * 64) / T) bnp_vm_kernel(VmArgs a
         for (int k = 1; k < BNP_MAX_PHASES; k++)
             if (phase == (u32)k) pc = args.prog[k];
         u64 ins = __ldg(pc++);
-        for (;;) {
+        bool running = true;
+        while (running) {
             const u32 lo = (u32)ins, hi = (u32)(ins >> 32);
             const u32 op = lo & 0xffu, d = (lo >> 8) & 0xffu, a = (lo >> 16) & 0xffu, b = lo >> 24;
             const u32 c = hi & 0xffu, ee = (hi >> 8) & 0xffu, imm = hi >> 16;
-            if (op == BNP_OP_END) break;
-            if (op == BNP_OP_MUL || op == BNP_OP_SQR || op == BNP_OP_MULFP) {
-                vm_product<T>(S, op, pc, ins, d, a, b, c, ee, imm);
-                continue;
-            }
-            if (op == BNP_OP_LIN) {  // d = LIN(slots), a = number of entry pairs
-                const u32 nw = (a + 1u) >> 1;
-                const u64 nx = __ldg(pc + nw);
-                Fp2 o;
-                vm_lin<T>(S, o, a, pc);
-                S.store(d, o);
-                ins = nx;
-                pc += nw + 1;
-                continue;
-            }
-            const u64 nxt = __ldg(pc++);  // prefetch (every program ends with END followed by padding)
+            // the word after the instruction: its extension word, its first entry word, or the next instruction
+            // (every program ends with END followed by padding)
+            const u64 w0 = __ldg(pc);
             Fp2 x, y, r;
+            // one dense switch: a jump table instead of a ladder of compares (the sequencer runs ~20 000
+            // instructions per pairing; the ladder was 10 % of all stall samples)
             switch (op) {
+                case BNP_OP_END:
+                    running = false;
+                    break;
+                case BNP_OP_MUL:
+                case BNP_OP_SQR:
+                case BNP_OP_MULFP:
+                    vm_product<T>(S, op, pc, ins, w0, d, a, b, c, ee, imm);
+                    break;
+                case BNP_OP_LIN: {  // d = LIN(slots), a = number of entry pairs
+                    const u32 nw = (a + 1u) >> 1;
+                    const u64 nx = __ldg(pc + nw);
+                    vm_lin<T>(S, r, a, pc);
+                    S.store(d, r);
+                    ins = nx;
+                    pc += nw + 1;
+                    break;
+                }
                 case BNP_OP_LDC:
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
@@ -385,11 +396,15 @@ __global__ void __launch_bounds__(T, (BNP_MINB * 64) / T) bnp_vm_kernel(VmArgs a
                         r.c1[i] = BNP_CONSTS[imm][8 + i];
                     }
                     S.store(d, r);
+                    ins = w0;
+                    pc++;
                     break;
                 case BNP_OP_LDG:
                     ldg_fp(r.c0, args.arr[imm], a, stride, e);
                     ldg_fp(r.c1, args.arr[imm], b, stride, e);
                     S.store(d, r);
+                    ins = w0;
+                    pc++;
                     break;
                 case BNP_OP_STG:
                     S.load(x, a);
@@ -397,6 +412,8 @@ __global__ void __launch_bounds__(T, (BNP_MINB * 64) / T) bnp_vm_kernel(VmArgs a
                         stg_fp(args.arr[imm], d, stride, e, x.c0);
                         stg_fp(args.arr[imm], b, stride, e, x.c1);
                     }
+                    ins = w0;
+                    pc++;
                     break;
                 case BNP_OP_SPILL: {
                     const uint4* p = S.base + a * (4 * T);
@@ -405,6 +422,8 @@ __global__ void __launch_bounds__(T, (BNP_MINB * 64) / T) bnp_vm_kernel(VmArgs a
                     q[total] = p[T];
                     q[2 * (size_t)total] = p[2 * T];
                     q[3 * (size_t)total] = p[3 * T];
+                    ins = w0;
+                    pc++;
                     break;
                 }
                 case BNP_OP_FILL: {
@@ -417,49 +436,66 @@ __global__ void __launch_bounds__(T, (BNP_MINB * 64) / T) bnp_vm_kernel(VmArgs a
                     p[T] = q1;
                     p[2 * T] = q2;
                     p[3 * T] = q3;
+                    ins = w0;
+                    pc++;
                     break;
                 }
                 case BNP_OP_INV:  // once or twice per program
                     S.load(x, a);
                     fp2_inv(r, x);
                     S.store(d, r);
+                    ins = w0;
+                    pc++;
                     break;
                 case BNP_OP_ADD:
                     S.load(x, a);
                     S.load(y, b);
                     fp2_add(r, x, y);
                     S.store(d, r);
+                    ins = w0;
+                    pc++;
                     break;
                 case BNP_OP_SUB:
                     S.load(x, a);
                     S.load(y, b);
                     fp2_sub(r, x, y);
                     S.store(d, r);
+                    ins = w0;
+                    pc++;
                     break;
                 case BNP_OP_DBL:
                     S.load(x, a);
                     fp2_add(r, x, x);
                     S.store(d, r);
+                    ins = w0;
+                    pc++;
                     break;
                 case BNP_OP_NEG:
                     S.load(x, a);
                     fp2_neg(r, x);
                     S.store(d, r);
+                    ins = w0;
+                    pc++;
                     break;
                 case BNP_OP_CONJ:
                     S.load(x, a);
                     fp2_conj(r, x);
                     S.store(d, r);
+                    ins = w0;
+                    pc++;
                     break;
                 case BNP_OP_MULXI:
                     S.load(x, a);
                     fp2_mul_xi(r, x);
                     S.store(d, r);
+                    ins = w0;
+                    pc++;
                     break;
                 default:
+                    ins = w0;
+                    pc++;
                     break;
             }
-            ins = nxt;
         }
         if (args.n_phases > 1u) {  // publish: this chunk's state is complete up to and including `phase`
             __threadfence();
