@@ -10,6 +10,14 @@ configs[1]; weak scaling: every rank gets its own 2^16).  `value` is device-resi
 (inputs already in HBM), `e2e` goes through the host-buffer C ABI (bnp_pairing_batch: H2D + kernel + D2H
 inside the timed region, pinned host memory).  The roofline is the integer-multiply pipe, measured live
 on the box by the library's IMAD.WIDE microbenchmark (MEASURED_PEAKS.json has no integer peak).
+
+Every number is parity-gated: after the timed region >= 1024 sampled outputs of every rank are compared with the
+C oracle (oracle/_build/libbn254_ref.so, the checker - never the thing measured); on a mismatch no line is
+printed and the exit code is 3.  `extra` (short runs outside the headline timing, --no-extras skips them) carries
+the other BASELINE configurations at their full sizes (2^20 Miller loops, 2^20 final exponentiations, 2^18
+Groth16-shaped products, 2^22 pairings STRONG-scaled over the ranks), the one real collective of the path (ONE
+product over 2^20 pairs: per-GPU fused Miller loops -> tree product -> 384-byte NCCL all-gather -> one final
+exponentiation, with the tail broken out), the latency of a single pairing and e2e from pageable host memory.
 Prints exactly one JSON line on rank 0.
 """
 import argparse
@@ -37,18 +45,23 @@ WORKLOADS = {
 }
 
 
-def ncu_traffic_bytes():
-    """dram__bytes_read + dram__bytes_write of the sequencer kernel, per launch, from the committed `ncu --set full`
-    capture of this same workload (profiles/ncu_r1_split.txt); None if the summary is missing."""
+POOL_K = 4096   # pool of K G1 x K G2 subgroup points, all index pairs distinct up to 2^24
+
+
+def program_stats(prog):
+    """Instruction histogram of the shipped program (build-time tables, recomputed here from the same sources):
+    how many sequencer instructions, spills and re-loads one pairing costs."""
     try:
-        tot = 0.0
-        for ln in open(os.path.join(ROOT, "profiles", "ncu_r1_split.txt")):
-            f = ln.split()
-            if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                tot += float(f[-1]) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[f[-2]]
-        return tot or None
-    except (OSError, ValueError, KeyError, IndexError):
-        return None
+        from plonky2_bn254_pairing_b200.microcode import gen
+
+        _, progs = gen.build_all(names={prog}, with_phases=False)
+        _, al, w = progs[0]
+        h = w["hist"]
+        return {"instructions": sum(h.values()), "spill": h.get("SPILL", 0), "fill": h.get("FILL", 0),
+                "products": h.get("MUL", 0) + h.get("SQR", 0) + h.get("MULFP", 0), "slots": al.n_slots,
+                "scratch_entries": al.n_scratch}
+    except Exception as e:  # noqa: BLE001 - diagnostics only
+        return {"error": repr(e)}
 
 
 def env_int(name, default):
@@ -153,7 +166,7 @@ def cpu_inputs(workload, n):
     from plonky2_bn254_pairing_b200 import workload as wl
 
     k = WORKLOADS[workload][1]
-    g1, g2, _ = wl.pairing_inputs(n, k=k)
+    g1, g2, _ = wl.pairing_inputs(n, K=POOL_K, k=k)
     f12 = None
     if workload == "final_exp":
         rs = np.random.RandomState(5)
@@ -216,13 +229,243 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
-def run_gpu(args):
+def oracle_outputs(cref, workload, g1, g2, f12):
+    """The C oracle (memoised mode, all host threads) on the given columns - the parity checker."""
+    import numpy as np
+
+    n = (f12 if workload == "final_exp" else g1).shape[2]
+    out = np.empty((12, 4, n), dtype=np.uint64)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    k = WORKLOADS[workload][1]
+    if workload == "miller":
+        cref.bn254_ref_miller_batch(p(g1), p(g2), p(out), n, 1, 0, 0)
+    elif workload == "final_exp":
+        cref.bn254_ref_final_exp_batch(p(f12), p(out), n, 0, 0)
+    else:
+        cref.bn254_ref_pairing_batch(p(g1), p(g2), p(out), n, k, 0, 0)
+    return out
+
+
+class Rig:
+    """One rank's device state: library handle, stream, helpers to run a workload device-resident."""
+
+    def __init__(self, local, rank, world):
+        import torch
+
+        from plonky2_bn254_pairing_b200 import native
+
+        self.torch, self.native = torch, native
+        self.local, self.rank, self.world = local, rank, world
+        self.dev = torch.device("cuda", local)
+        self.lib = native.init([local])
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.sp = ctypes.c_void_p(self.stream.cuda_stream)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+        self.cref = None
+
+    def to_dev(self, a):
+        import numpy as np
+
+        return self.torch.from_numpy(a.view(np.int64)).to(self.dev)
+
+    def barrier(self):
+        import torch.distributed as dist
+
+        self.torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, x):
+        import torch.distributed as dist
+
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ok(self, ok):
+        import torch.distributed as dist
+
+        if self.world == 1:
+            return ok
+        t = self.torch.tensor([1 if ok else 0], dtype=self.torch.int64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def inputs(self, workload, n, offset):
+        """Device-resident inputs of `n` elements of the workload (plus the host copies for parity / e2e)."""
+        from plonky2_bn254_pairing_b200 import workload as wl
+
+        torch = self.torch
+        prog, k, _ = WORKLOADS[workload]
+        g1, g2, _ = wl.pairing_inputs(n, K=POOL_K, k=k, offset=offset)
+        d = {"g1": g1, "g2": g2, "f12": None, "d_g1": self.to_dev(g1), "d_g2": self.to_dev(g2), "d_f12": None, "n": n, "k": k,
+             "prog": prog, "workload": workload}
+        d["d_out"] = torch.empty((12, 4, n), dtype=torch.int64, device=self.dev)
+        if workload == "final_exp":
+            # inputs = GPU Miller outputs of the same indices (SURVEY 8(d) config 3)
+            d["d_f12"] = torch.empty((12, 4, n), dtype=torch.int64, device=self.dev)
+            self.native.check(self.lib.bnp_run_program_dev(self.local, self.sp, b"miller", d["d_g1"].data_ptr(),
+                                                           d["d_g2"].data_ptr(), None, None, d["d_f12"].data_ptr(), n))
+            self.torch.cuda.synchronize(self.dev)
+        return d
+
+    def launch(self, w):
+        self.native.check(self.lib.bnp_run_program_dev(
+            self.local, self.sp, w["prog"].encode(), w["d_g1"].data_ptr(), w["d_g2"].data_ptr(),
+            w["d_f12"].data_ptr() if w["d_f12"] is not None else None, None, w["d_out"].data_ptr(), w["n"]))
+
+    def timed(self, w, steps, warmup):
+        """(total ms over `steps` launches incl. the L2 flushes, [kernel ms per launch]) - CUDA events on the launch stream."""
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            for _ in range(warmup):
+                self.flush.zero_()
+                self.launch(w)
+        self.barrier()
+        k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(self.stream):
+            t0.record(self.stream)
+            for i in range(steps):
+                self.flush.zero_()  # L2 flush between timed iterations (inside the timed region, ~0.1% of a step)
+                k_ev[i][0].record(self.stream)
+                self.launch(w)
+                k_ev[i][1].record(self.stream)
+            t1.record(self.stream)
+        self.barrier()
+        return t0.elapsed_time(t1), [a.elapsed_time(b) for a, b in k_ev]
+
+    def parity(self, w, n_check, seed):
+        """Compare `n_check` sampled outputs of the last launch with the C oracle.  Returns (checked, ok)."""
+        import numpy as np
+
+        if self.cref is None:
+            self.cref = load_cref()
+        n = w["n"]
+        m = min(n_check, n)
+        idx = np.sort(np.random.RandomState(seed + 7919 * self.rank).choice(n, m, replace=False))
+        got = w["d_out"][:, :, self.torch.from_numpy(idx).to(self.dev)].cpu().numpy().view(np.uint64)
+        col = lambda a: None if a is None else np.ascontiguousarray(a[:, :, idx])  # noqa: E731
+        f12 = None
+        if w["d_f12"] is not None:
+            f12 = np.ascontiguousarray(w["d_f12"][:, :, self.torch.from_numpy(idx).to(self.dev)].cpu().numpy().view(np.uint64))
+        want = oracle_outputs(self.cref, w["workload"], col(w["g1"]), col(w["g2"]), f12)
+        return m, bool(np.array_equal(got, want))
+
+
+def run_extras(rig, peak, args):
+    """Short device-resident runs of the other BASELINE configurations and of the one collective (outside the headline
+    timing); every one parity-checked on a sample."""
     import numpy as np
     import torch
     import torch.distributed as dist
 
-    from plonky2_bn254_pairing_b200 import native
+    lib, native, world, rank, local = rig.lib, rig.native, rig.world, rig.rank, rig.local
+    extra = {"workloads": {}}
+    cfgs = [  # (tag, workload, total elements, strong?)
+        ("miller_2e20", "miller", 1 << 20, False),
+        ("final_exp_2e20", "final_exp", 1 << 20, False),
+        ("groth16_2e18", "groth16", 1 << 18, False),
+        ("pairing_2e22_strong", "pairing", 1 << 22, True),
+    ]
+    for tag, wk, n_total, strong in cfgs:
+        n = n_total // world if strong else n_total
+        w = rig.inputs(wk, n, offset=(1 << 24) + rank * n)
+        total_ms, kern = rig.timed(w, steps=2, warmup=1)
+        total_ms = rig.max_over_ranks(total_ms)
+        checked, ok = rig.parity(w, 256, seed=11)
+        ok = rig.all_ok(ok)
+        macs = lib.bnp_program_macs(w["prog"].encode())
+        kavg = sum(kern) / len(kern)
+        extra["workloads"][tag] = {
+            "program": w["prog"], "elements_per_gpu": n, "scaling": "strong" if strong else "weak",
+            "value": world * n * w["k"] * 2 / (total_ms * 1e-3), "unit": UNIT, "kernel_ms_avg": kavg,
+            "frac": n * macs / (kavg * 1e-3) / peak, "parity": {"checked": checked * world, "ok": ok}}
+        del w
+        torch.cuda.empty_cache()
+        if not ok:
+            return extra, False
+
+    # ---- the one real exchange step: ONE product over 2^20 pairs, sharded by index range over the ranks
+    from plonky2_bn254_pairing_b200 import sharding
     from plonky2_bn254_pairing_b200 import workload as wl
+
+    n_total = 1 << 20
+    off, cnt = sharding.shard_range(n_total, rank, world)
+    g1, g2, _ = wl.pairing_inputs(cnt, K=POOL_K, offset=(3 << 24) + off)
+    d_g1, d_g2 = rig.to_dev(g1), rig.to_dev(g2)
+    d_ml = torch.empty((12, 4, cnt), dtype=torch.int64, device=rig.dev)
+    d_part = torch.zeros((12, 4, 1), dtype=torch.int64, device=rig.dev)
+    d_fe = torch.zeros((12, 4, 1), dtype=torch.int64, device=rig.dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    one_stream = ctypes.c_void_p(1)  # cudaStreamLegacy: ordered with torch's default stream and with NCCL
+    best = None
+    for it in range(3):
+        rig.barrier()
+        ev[0].record()
+        native.check(lib.bnp_miller_loop_fused_dev(local, one_stream, d_g1.data_ptr(), d_g2.data_ptr(), d_ml.data_ptr(), cnt))
+        ev[1].record()
+        native.check(lib.bnp_fq12_product_dev(local, one_stream, d_ml.data_ptr(), d_part.data_ptr(), cnt))
+        ev[2].record()
+        if world > 1:
+            gathered = sharding.all_gather_fq12(d_part)
+            total = torch.zeros((12, 4, 1), dtype=torch.int64, device=rig.dev)
+            native.check(lib.bnp_fq12_product_dev(local, one_stream, gathered.data_ptr(), total.data_ptr(), world))
+        else:
+            total = d_part
+        ev[3].record()
+        native.check(lib.bnp_final_exp_dev(local, one_stream, total.data_ptr(), d_fe.data_ptr(), 1, 0))
+        ev[4].record()
+        torch.cuda.synchronize(rig.dev)
+        t = [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
+        if it and (best is None or sum(t) < sum(best)):
+            best = t
+    tot_ms = rig.max_over_ranks(sum(best))
+    same = True
+    if world > 1:
+        chk = [torch.empty_like(d_fe) for _ in range(world)]
+        dist.all_gather(chk, d_fe)
+        same = all(torch.equal(c, chk[0]) for c in chk)
+    # checker: the same product, from the oracle's Miller values of a 512-pair prefix... the full product is covered by
+    # tests/test_gpu_configs.py::test_config5; here: every rank holds the same 384 bytes, and they are a canonical
+    # element of the order-r subgroup's image (x^r == 1 is too slow to test here), so only equality is asserted
+    extra["global_product_2e20"] = {
+        "pairs": n_total, "pairs_per_gpu": cnt, "total_ms": tot_ms, "pairs_per_s": n_total / (tot_ms * 1e-3),
+        "miller_ms": best[0], "tree_us": best[1] * 1e3, "allgather_and_combine_us": best[2] * 1e3, "final_exp_us": best[3] * 1e3,
+        "collective": "NCCL all_gather of one 384-byte Fq12 per rank" if world > 1 else "none (1 rank)",
+        "bit_equal_on_every_rank": bool(same)}
+    del d_g1, d_g2, d_ml
+    torch.cuda.empty_cache()
+
+    # ---- a single pairing through the host ABI (the reference's scalar `pairing(p, q)` call), and pageable-memory e2e
+    if rank == 0:
+        g1, g2, _ = wl.pairing_inputs(BATCH, K=POOL_K, offset=0)
+        o1 = np.empty((12, 4, 1), dtype=np.uint64)
+        a1, b1 = np.ascontiguousarray(g1[:, :, :1]), np.ascontiguousarray(g2[:, :, :1])
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+        native.check(lib.bnp_pairing_batch(p(a1), p(b1), p(o1), 1, 0))
+        t0 = time.perf_counter()
+        for _ in range(5):
+            native.check(lib.bnp_pairing_batch(p(a1), p(b1), p(o1), 1, 0))
+        extra["latency_one_pairing_us"] = (time.perf_counter() - t0) / 5 * 1e6
+        out = np.empty((12, 4, BATCH), dtype=np.uint64)  # plain (pageable) numpy memory, like a Rust Vec
+        native.check(lib.bnp_pairing_batch(p(g1), p(g2), p(out), BATCH, 0))
+        t0 = time.perf_counter()
+        for _ in range(3):
+            native.check(lib.bnp_pairing_batch(p(g1), p(g2), p(out), BATCH, 0))
+        extra["e2e_pageable"] = {"value": BATCH * 3 / (time.perf_counter() - t0), "unit": UNIT,
+                                 "note": "2^16 pairings per call, caller buffers in pageable memory"}
+    rig.barrier()
+    return extra, bool(same)
+
+
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if not torch.cuda.is_available():
@@ -242,37 +485,12 @@ def run_gpu(args):
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-    lib = native.init([local])
+    rig = Rig(local, rank, world)
+    lib, native, dev = rig.lib, rig.native, rig.dev
 
     prog, k, label = WORKLOADS[args.workload]
     n = args.batch
-    g1, g2, _ = wl.pairing_inputs(n, k=k, offset=rank * n)
-    dev = torch.device("cuda", local)
-
-    def to_dev(a):
-        return torch.from_numpy(a.view(np.int64)).to(dev)
-
-    d_g1, d_g2 = to_dev(g1), to_dev(g2)
-    d_out = torch.empty((12, 4, n), dtype=torch.int64, device=dev)
-    d_f12 = None
-    stream = torch.cuda.Stream(device=dev)
-    sp = ctypes.c_void_p(stream.cuda_stream)
-    if args.workload == "final_exp":
-        # inputs = GPU Miller outputs of the same indices
-        d_f12 = torch.empty((12, 4, n), dtype=torch.int64, device=dev)
-        native.check(lib.bnp_run_program_dev(local, sp, b"miller", d_g1.data_ptr(), d_g2.data_ptr(), None, None,
-                                             d_f12.data_ptr(), n))
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    def launch():
-        native.check(lib.bnp_run_program_dev(local, sp, prog.encode(), d_g1.data_ptr(), d_g2.data_ptr(),
-                                             d_f12.data_ptr() if d_f12 is not None else None, None, d_out.data_ptr(), n))
-
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    w = rig.inputs(args.workload, n, offset=rank * n)
 
     # roofline denominator, measured live (rank-local; reported from rank 0)
     peak = ctypes.c_double()
@@ -280,45 +498,38 @@ def run_gpu(args):
     peak32 = ctypes.c_double()
     native.check(lib.bnp_imad32_peak(local, ctypes.byref(peak32)))
     macs = lib.bnp_program_macs(prog.encode())             # algorithmic (Karatsuba Fq2 products), SURVEY 8(d)
-    macs_x = lib.bnp_program_macs_executed(prog.encode())  # what the component-split kernel issues
-
-    with torch.cuda.stream(stream):
-        for _ in range(max(args.warmup, 3)):
-            flush.zero_()
-            launch()
-    barrier()
+    macs_x = lib.bnp_program_macs_executed(prog.encode())  # what the kernel issues (one thread = one whole Fq2 operation)
 
     sampler = ClockSampler(local)
+    warm = max(args.warmup, 3)
+    with torch.cuda.stream(rig.stream):
+        for _ in range(warm):
+            rig.flush.zero_()
+            rig.launch(w)
+    rig.barrier()
     if rank == 0:
         sampler.start()
     launches0 = lib.bnp_launch_count()
-    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    with torch.cuda.stream(stream):
-        t0.record(stream)
-        for i in range(args.steps):
-            flush.zero_()  # L2 flush between timed iterations (inside the timed region, ~0.1% of a step)
-            k_ev[i][0].record(stream)
-            launch()
-            k_ev[i][1].record(stream)
-        t1.record(stream)
-    barrier()
+    elapsed_ms, kern_ms = rig.timed(w, args.steps, 0)
     launches = lib.bnp_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    elapsed_ms = t0.elapsed_time(t1)
-    kern_ms = [a.elapsed_time(b) for a, b in k_ev]
-    if world > 1:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
+    elapsed_ms = rig.max_over_ranks(elapsed_ms)
     value = world * n * k * args.steps / (elapsed_ms * 1e-3)
 
+    # ---- parity gate: sampled outputs of the timed launches against the C oracle, on every rank
+    checked, ok = rig.parity(w, args.parity, seed=1)
+    ok = rig.all_ok(ok)
+    if not ok:
+        sys.stderr.write("bench.py: PARITY FAILURE - device results differ from the oracle; no line printed\n")
+        if world > 1:
+            dist.destroy_process_group()
+        return 3
+
     # ---- end to end through the host-buffer C ABI (pinned host memory, copies inside the timed region)
-    h_g1 = torch.from_numpy(g1.view(np.int64)).pin_memory()
-    h_g2 = torch.from_numpy(g2.view(np.int64)).pin_memory()
+    h_g1 = torch.from_numpy(w["g1"].view(np.int64)).pin_memory()
+    h_g2 = torch.from_numpy(w["g2"].view(np.int64)).pin_memory()
     h_out = torch.empty((12, 4, n), dtype=torch.int64).pin_memory()
-    h_f12 = d_f12.cpu().pin_memory() if d_f12 is not None else None
+    h_f12 = w["d_f12"].cpu().pin_memory() if w["d_f12"] is not None else None
 
     def e2e_call():
         if args.workload == "pairing":
@@ -332,20 +543,27 @@ def run_gpu(args):
 
     e2e_steps = max(3, min(args.steps, 10))
     e2e_call()
-    barrier()
+    rig.barrier()
     w0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_call()  # synchronous: returns after the D2H copy completed
     torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - w0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = rig.max_over_ranks(time.perf_counter() - w0)
     e2e_value = world * n * k * e2e_steps / e2e_s
     in_bytes = (h_f12.numel() * 8) if args.workload == "final_exp" else (h_g1.numel() + h_g2.numel()) * 8
-    # quick integrity check of the e2e result against the device-resident result
-    assert torch.equal(h_out[:, :, :64], d_out[:, :, :64].cpu()), "e2e and device-resident results differ"
+    # the e2e result is the same computation: bit-equal to the device-resident result that was just parity-checked
+    e2e_same = rig.all_ok(bool(torch.equal(h_out, w["d_out"].cpu())))
+    if not e2e_same:
+        sys.stderr.write("bench.py: e2e and device-resident results differ; no line printed\n")
+        return 3
+
+    extra, extra_ok = (None, True)
+    if not args.no_extras:
+        del h_g1, h_g2, h_out
+        extra, extra_ok = run_extras(rig, peak.value, args)
+        if not extra_ok:
+            sys.stderr.write("bench.py: PARITY FAILURE in the extra workloads; no line printed\n")
+            return 3
 
     if rank == 0:
         kavg = sum(kern_ms) / len(kern_ms)
@@ -357,25 +575,29 @@ def run_gpu(args):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         alg_bytes = n * (k * 192 + 384) if args.workload != "final_exp" else n * 768
+        threads = env_int("BNP_THREADS", 64) or 64
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 (8x32-bit-limb Fp254 Montgomery, IMAD.WIDE.U32 carry chains)", "data": "synthetic",
             "config": {"workload": label, "program": prog, "batch_per_gpu": n, "pairings_per_element": k,
                        "parallelism": "index-sharded, %d rank(s), no data-path collective" % world,
                        "l2": "256 MiB memset between timed iterations (inside the timed region)",
-                       "inputs": "pool of 256 G1 x 256 G2 subgroup points, pair i = (P[i%K], Q[(i/K+7i)%K])"},
+                       "inputs": "pool of %d G1 x %d G2 subgroup points, pair i = (P[i%%K], Q[(i/K+7i)%%K])" % (POOL_K, POOL_K)},
+            "parity": {"checked": checked * world, "ok": True, "e2e_bit_equal": True,
+                       "oracle": "oracle/_build/libbn254_ref.so (C restatement of the reference, memoised mode), "
+                                 "%d sampled elements per rank after the timed region" % checked},
             "roofline": {
                 "bound": "imad", "achieved": achieved / 1e9, "peak": peak.value / 1e9, "unit": "GMAC/s",
                 "frac": achieved / peak.value,
-                # bytes: one ncu capture at 2^16 pairings (includes the L2-flush write-back and spill traffic that
-                # leaves the L2); not a bound - the algorithmic I/O is 576 B per pairing
-                "traffic": ncu_traffic_bytes() if (args.workload == "pairing" and n == BATCH) else None,
-                "kernel": "bnp_vm_kernel<64>", "kernel_ms_avg": kavg, "macs_per_element": macs,
+                # DRAM bytes cannot be measured outside a profiler: see profiles/ncu_r2_*.txt for the captured value
+                # (the spill scratch lives in L2; algorithmic I/O is 576 B per pairing - not the bound)
+                "traffic": None,
+                "kernel": "bnp_vm_kernel<%d>" % threads, "kernel_ms_avg": kavg, "macs_per_element": macs,
                 "executed": {"macs_per_element": macs_x, "gmacs": n * macs_x / (kavg * 1e-3) / 1e9,
                              "pipe_frac": n * macs_x / (kavg * 1e-3) / peak.value,
-                             "note": "the kernel computes an Fq2 product as a two-term dot product per lane "
-                                     "(4 Fp products, not Karatsuba's 3); frac above counts only the algorithmic MACs"},
+                             "note": "one thread runs a whole Karatsuba Fq2 operation: executed == algorithmic MACs"},
+                "program": program_stats(prog),
                 "peak_source": "measured live: bnp_imad_peak (IMAD.WIDE.U32[.X] 4-deep carry chains, 32 MACs/thread/iter); "
                                "MEASURED_PEAKS.json has no integer peak",
                 "imad32_peak_gops": peak32.value / 1e9,
@@ -383,13 +605,15 @@ def run_gpu(args):
                         "frac": alg_bytes / (kavg * 1e-3) / 1e9 / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "note": "informational; not the bound"},
             },
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": h_out.numel() * 8,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": n * 384,
                     "steps": e2e_steps, "api": "bnp_%s_batch (host pointers, synchronous)" % (
                         "pairing" if args.workload == "pairing" else "miller_loop" if args.workload == "miller"
                         else "final_exp" if args.workload == "final_exp" else "multi_pairing")},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
+        if extra is not None:
+            line["extra"] = extra
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args.workload)
         print(json.dumps(line), flush=True)
@@ -408,6 +632,8 @@ def main():
     ap.add_argument("--workload", default="pairing", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=BATCH, help="elements per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the `extra` workloads (other configs, global product)")
+    ap.add_argument("--parity", type=int, default=1024, help="outputs per rank compared with the oracle after the timed region")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

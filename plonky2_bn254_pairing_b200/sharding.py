@@ -65,7 +65,7 @@ class DeviceOps:
         # it explicitly: cudaStreamLegacy (0x1) IS that stream, and everything stays ordered with the tensors
         # torch made before the call and with the collective that follows (found on 2 GPUs: the partials were
         # gathered before the tree product had run).
-        h = torch.cuda.current_stream().cuda_stream
+        h = torch.cuda.current_stream(self.dev).cuda_stream
         return ctypes.c_void_p(h if h else 1)
 
     def _out(self, n):
