@@ -228,20 +228,28 @@ __device__ __noinline__ void fp_inv(u32* r, const u32* a) {
     // acc = 1 in Montgomery form = R mod p
     acc[0] = 0xc58f0d9du; acc[1] = 0xd35d438du; acc[2] = 0xf5c70b3du; acc[3] = 0x0a78eb28u;
     acc[4] = 0x7879462cu; acc[5] = 0x666ea36fu; acc[6] = 0x9a07df2fu; acc[7] = 0x0e0a77c1u;
-    // left-to-right binary ladder; the exponent is a constant, so the multiply branch is uniform
-    // across the whole grid (no divergence).  254 squarings + popcount(p-2) multiplications.
+    // left-to-right binary ladder, 254 squarings + popcount(p-2) multiplications.  The exponent is a constant, so the
+    // schedule is the same for the whole grid; squaring and multiplication share ONE fp_mul body in the instruction
+    // stream (the second factor is selected), because this loop runs 381 times per pairing and the kernel's warm code
+    // has to fit the 32 KB instruction cache.
+    int bit = 253;
+    bool mul_step = false;
 #pragma unroll 1
-    for (int bit = 253; bit >= 0; bit--) {
-        u32 t[8];
-        fp_mul(t, acc, acc);
-        u32 w = e[0];
+    while (bit >= 0) {
+        u32 f[8], t[8];
 #pragma unroll
-        for (int k = 1; k < 8; k++) w = ((bit >> 5) == k) ? e[k] : w;  // no dynamic register indexing
-        if ((w >> (bit & 31)) & 1u) {
-            fp_mul(acc, t, base);
+        for (int i = 0; i < 8; i++) f[i] = mul_step ? base[i] : acc[i];
+        fp_mul(t, acc, f);
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = t[i];
+        if (mul_step) {
+            mul_step = false;
+            bit--;
         } else {
+            u32 w = e[0];
 #pragma unroll
-            for (int i = 0; i < 8; i++) acc[i] = t[i];
+            for (int k = 1; k < 8; k++) w = ((bit >> 5) == k) ? e[k] : w;  // no dynamic register indexing
+            if ((w >> (bit & 31)) & 1u) mul_step = true; else bit--;
         }
     }
 #pragma unroll
