@@ -20,6 +20,8 @@ extern "C" {
     pub fn bnp_pairing_product(g1: *const u64, g2: *const u64, out: *mut u64, n: usize, variant: c_int) -> c_int;
     pub fn bnp_frobenius_batch(input: *const u64, out: *mut u64, n: usize, power: usize) -> c_int;
     pub fn bnp_fq12_mul_batch(a: *const u64, b: *const u64, out: *mut u64, n: usize) -> c_int;
+    /// pow_native (final_exp_native.rs:56): `exp` = n_limbs little-endian u64 limbs shared by the batch
+    pub fn bnp_pow_u64_batch(input: *const u64, out: *mut u64, n: usize, exp: *const u64, n_limbs: usize) -> c_int;
     pub fn bnp_pairing_dev(device: c_int, stream: *mut c_void, g1: *const u64, g2: *const u64, out: *mut u64,
                            n: usize, k: c_int, variant: c_int) -> c_int;
 }

@@ -5,6 +5,9 @@
 //!   multi_miller_loop_native  <- src/miller_loop_native.rs:324
 //!   final_exp_native          <- src/final_exp_native.rs:209
 //!   frobenius_map_native      <- src/final_exp_native.rs:17
+//!   pow_native                <- src/final_exp_native.rs:56
+//!   get_naf, frob_coeffs      <- src/final_exp_native.rs:86, :183   (host-side table generators; final_exp_target.rs:18 imports frob_coeffs)
+//!   conjugate_fp2, neg_conjugate_fp2 <- src/miller_loop_native.rs:284, :291
 //!   pairing                   <- src/pairing.rs:20
 //!
 //! Marshalling: ark's `Fq` is `Fp(BigInt<4>([u64; 4]), _)` in Montgomery form with R = 2^256 - exactly the
@@ -134,12 +137,17 @@ pub fn final_exp_witness_batch(fs: &[MyFq12]) -> Vec<FinalExpWitness> {
 }
 
 pub fn pairing_batch(ps: &[G1Affine], qs: &[G2Affine]) -> Vec<Fq12> {
+    pairing_batch_variant(ps, qs, ffi::BNP_VARIANT_REFERENCE)
+}
+
+/// variant 0: the reference's exponent (p^12-1)/r; variant 1: ark-ec 0.4.2's `Bn254::pairing` exponent.
+pub fn pairing_batch_variant(ps: &[G1Affine], qs: &[G2Affine], variant: i32) -> Vec<Fq12> {
     assert_eq!(qs.len(), ps.len());
     init();
     let n = ps.len();
     let (g1, g2) = (pack_g1(ps), pack_g2(qs));
     let mut out = vec![0u64; 48 * n];
-    check(unsafe { ffi::bnp_pairing_batch(g1.as_ptr(), g2.as_ptr(), out.as_mut_ptr(), n, ffi::BNP_VARIANT_REFERENCE) });
+    check(unsafe { ffi::bnp_pairing_batch(g1.as_ptr(), g2.as_ptr(), out.as_mut_ptr(), n, variant) });
     unpack_fq12(&out, n).into_iter().map(Into::into).collect() // MyFq12 -> Fq12, as pairing.rs:21
 }
 
@@ -210,6 +218,71 @@ pub fn frobenius_map_native(a: MyFq12, power: usize) -> MyFq12 {
 
 pub fn pairing(p: G1Affine, q: G2Affine) -> Fq12 {
     pairing_batch(&[p], &[q]).remove(0)
+}
+
+/// `a^exp` for any `a` (final_exp_native.rs:56-84), `exp` little-endian u64 limbs.  Same quirk as the reference for a
+/// zero exponent: its accumulator starts at `a` and the loop never starts, so `a` itself comes back.
+pub fn pow_native_batch(fs: &[MyFq12], exp: &[u64]) -> Vec<MyFq12> {
+    init();
+    let n = fs.len();
+    let inp = pack_fq12(fs);
+    let mut out = vec![0u64; 48 * n];
+    check(unsafe { ffi::bnp_pow_u64_batch(inp.as_ptr(), out.as_mut_ptr(), n, exp.as_ptr(), exp.len()) });
+    unpack_fq12(&out, n)
+}
+
+pub fn pow_native(a: MyFq12, exp: Vec<u64>) -> MyFq12 {
+    pow_native_batch(core::slice::from_ref(&a), &exp).remove(0)
+}
+
+/// Signed-digit (non-adjacent form) expansion, least significant digit first (final_exp_native.rs:86-128).
+/// Pure host-side table generation - the GPU programs have the digits of BN_X and 6x+2 baked in at build time, and
+/// `bnp_pow_u64_batch` derives them itself - kept so that `use ...::get_naf` keeps compiling.
+pub fn get_naf(mut exp: Vec<u64>) -> Vec<i8> {
+    let mut naf: Vec<i8> = Vec::with_capacity(64 * exp.len());
+    let len = exp.len();
+    for idx in 0..len {
+        let mut e: u64 = exp[idx];
+        for _ in 0..64 {
+            if e & 1 == 1 {
+                let z = 2i8 - (e % 4) as i8;
+                e /= 2;
+                if z == -1 {
+                    e += 1;
+                }
+                naf.push(z);
+            } else {
+                naf.push(0);
+                e /= 2;
+            }
+        }
+        if e != 0 {
+            let mut j = idx + 1;
+            while j < exp.len() && exp[j] == u64::MAX {
+                exp[j] = 0;
+                j += 1;
+            }
+            if j < exp.len() {
+                exp[j] += 1;
+            } else {
+                exp.push(1);
+            }
+        }
+    }
+    // the reference asserts `len == exp.len() + 1` here (:123), which cannot hold once `exp` has grown: it panics on
+    // a carry out of the top limb, and so does this
+    assert!(exp.len() == len, "get_naf: carry out of the top limb");
+    naf
+}
+
+/// xi^((p^index - 1) / 6), xi = 9 + u (final_exp_native.rs:183-192; imported by final_exp_target.rs:18).
+pub fn frob_coeffs(index: usize) -> Fq2 {
+    use ark_ff::{Field, PrimeField};
+    use num_bigint::BigUint;
+    let modulus: BigUint = Fq::MODULUS.into();
+    let num = modulus.pow(index as u32) - 1u32;
+    let k = num / 6u32;
+    Fq2::new(Fq::from(9u64), Fq::from(1u64)).pow(k.to_u64_digits())
 }
 
 // conjugate_fp2 / neg_conjugate_fp2 (miller_loop_native.rs:284-296) are two field negations: kept on the CPU.

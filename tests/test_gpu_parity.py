@@ -277,7 +277,8 @@ def test_all_devices_in_one_process(lib):
     assert np.array_equal(acc, api.pairing_product_soa(np.ascontiguousarray(g1[:, :, :64]), np.ascontiguousarray(g2[:, :, :64])))
 
 
-# ----------------------------------------------------------------------------- BASELINE config 2: 2^16 pairings, every element
+# ----------------------------------------------------------------------------- 2^16 pairings: whole-batch properties
+# (every one of the 65 536 results is compared with the oracle in tests/test_gpu_configs.py::test_config2_*)
 def test_full_size_batch_bit_exact_and_properties(lib, cref):
     n = 1 << 16
     K = 256
@@ -287,8 +288,7 @@ def test_full_size_batch_bit_exact_and_properties(lib, cref):
     g1 = np.ascontiguousarray(api.pack_soa(api.g1_rows(Ps))[:, :, i1])
     g2 = np.ascontiguousarray(api.pack_soa(api.g2_rows(Qs))[:, :, i2])
     got = api.pairing_soa(g1, g2)
-    # all 65 536 index pairs are distinct combinations of the pool: check every one against the C oracle
-    # through the unique (i1, i2) -> result map computed once per distinct pair
+    # all 65 536 index pairs are distinct combinations of the pool; a sample of 4 096 against the C oracle here
     pairs, inv = np.unique(np.stack([i1, i2]), axis=1, return_inverse=True)
     assert pairs.shape[1] == n
     sample = np.random.RandomState(1).choice(n, 4096, replace=False)
