@@ -85,6 +85,13 @@ int bnp_frobenius_batch(const uint64_t* in, uint64_t* out, size_t n, size_t powe
  * a = 0 with a negative digit makes the reference panic (division by zero) - here that element comes back as 0.
  * exp = 0 returns a itself, like the reference (its accumulator starts at `a` and the loop never starts, :57,83). */
 int bnp_pow_u64_batch(const uint64_t* in, uint64_t* out, size_t n, const uint64_t* exp, size_t n_limbs);
+/* Input validation on the device: ok[e] = 1 iff the points of element e would be accepted by
+ * `G1Affine::new` / `G2Affine::new` - on the curve (G1: y^2 = x^3 + 3, cofactor 1) resp. on the twist
+ * y^2 = x^3 + 3/(9+u) AND in the r-torsion subgroup (ark-bn254 0.4's own test [6x^2]Q == psi(Q)).  This is the
+ * assertion hidden behind miller_loop_native.rs:303,311 that the pairing entry points do NOT re-check: they compute
+ * on whatever coordinates they are given.  g1 or g2 may be NULL (only the other group is checked); coordinates
+ * (0, 0) - ark's encoding of the identity, which carries a separate flag there - are reported as invalid. */
+int bnp_validate_batch(const uint64_t* g1 /* [2][4][n] */, const uint64_t* g2 /* [4][4][n] */, unsigned char* ok /* [n] */, size_t n);
 /* MyFq12 `Mul`: out = a * b element-wise. */
 int bnp_fq12_mul_batch(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
 
@@ -98,6 +105,7 @@ int bnp_final_exp_witness_dev(int device, void* stream, const uint64_t* in, uint
 int bnp_pairing_dev(int device, void* stream, const uint64_t* g1, const uint64_t* g2, uint64_t* out, size_t n, int k, int variant);
 int bnp_frobenius_dev(int device, void* stream, const uint64_t* in, uint64_t* out, size_t n, size_t power);
 int bnp_pow_u64_dev(int device, void* stream, const uint64_t* in, uint64_t* out, size_t n, const uint64_t* exp, size_t n_limbs);
+int bnp_validate_dev(int device, void* stream, const uint64_t* g1, const uint64_t* g2, unsigned char* ok /* device, [n] */, size_t n);
 int bnp_fq12_mul_dev(int device, void* stream, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
 /* In-place tree product of n MyFq12 values (buf[12][4][n], destroyed) -> out[12][4][1]. */
 int bnp_fq12_product_dev(int device, void* stream, uint64_t* buf, uint64_t* out, size_t n);
@@ -106,9 +114,8 @@ int bnp_fq12_product_dev(int device, void* stream, uint64_t* buf, uint64_t* out,
 /* Algorithmic work of one element of the named program ("pairing_v0", "miller", "final_exp_v0", ...):
  * 32x32->64 multiply-accumulates (64 per Fp product + 72 per Montgomery reduction), 0 if unknown. */
 uint64_t bnp_program_macs(const char* program);
-/* Multiply-accumulates the kernel actually issues for one element: the component-split kernel computes an Fq2
- * product as a two-term dot product per lane (4 Fp products per Fq2 product instead of Karatsuba's 3), so this
- * is larger than bnp_program_macs; the ratio of the two is the price paid for doubling the resident warps. */
+/* Multiply-accumulates the kernel actually issues for one element.  One thread runs a whole Karatsuba Fq2 operation,
+ * so this equals bnp_program_macs (round 1's component-split kernel issued 15 % more). */
 uint64_t bnp_program_macs_executed(const char* program);
 /* Kernel launches issued by this library since bnp_init (for bench.py's gpu_launches). */
 uint64_t bnp_launch_count(void);
@@ -120,8 +127,8 @@ int bnp_imad32_peak(int device, double* imads_per_s);
 /* Run an arbitrary sequencer program by name on device arrays (test hook for op-level parity). */
 int bnp_run_program_dev(int device, void* stream, const char* program, const uint64_t* g1, const uint64_t* g2,
                         const uint64_t* f12, const uint64_t* aux, uint64_t* out, size_t n);
-/* Tuning knobs (0 keeps the current setting): threads per block (32/64/96/128/256/512; two lanes work on one pairing,
- * blocks of 128 threads and more run their warps in lockstep behind a block barrier), and whether programs are run as
+/* Tuning knobs (0 keeps the current setting): threads per block (32/64/128/256; one thread per pairing), and whether
+ * programs are run as
  * phase-split task queues (1 = automatic: when the unsplit batch would leave the last round of warp-tasks badly
  * filled, 2 = never, 3 = whenever the library has a split variant of the program). */
 int bnp_set_launch_config(int threads_per_block, int phase_mode);

@@ -154,6 +154,16 @@ def pow_soa(f, exp):
     return out
 
 
+def validate_soa(g1=None, g2=None):
+    """uint8 flags [n]: 1 iff the element's points pass `G1Affine::new` / `G2Affine::new` (on-curve, G2 in the subgroup)."""
+    lib = native.lib()
+    n = (g1 if g1 is not None else g2).shape[2]
+    ok = np.zeros(n, dtype=np.uint8)
+    native.check(lib.bnp_validate_batch(_ptr(g1) if g1 is not None else None, _ptr(g2) if g2 is not None else None,
+                                        ok.ctypes.data_as(ctypes.c_void_p), n))
+    return ok
+
+
 # ----------------------------------------------------------------------------- batched slice variants (north star)
 def miller_loop_native_batch(Qs, Ps):
     """[miller_loop_native(Q_i, P_i)]"""
@@ -213,6 +223,16 @@ def pairing_product(pairs, variant=VARIANT_REFERENCE):
     g1 = pack_soa(g1_rows([p for (p, _) in pairs]))
     g2 = pack_soa(g2_rows([q for (_, q) in pairs]))
     return unpack_soa(pairing_product_soa(g1, g2, variant))[0]
+
+
+def validate_batch(Ps=None, Qs=None):
+    """[bool]: would `G1Affine::new(P_i)` / `G2Affine::new(Q_i)` accept the coordinates?  (The check the reference
+    gets from ark inside twisted_frobenius, miller_loop_native.rs:303,311; the pairing calls here do not repeat it.)"""
+    g1 = pack_soa(g1_rows(Ps)) if Ps else None
+    g2 = pack_soa(g2_rows(Qs)) if Qs else None
+    if g1 is None and g2 is None:
+        return []
+    return [bool(v) for v in validate_soa(g1, g2)]
 
 
 def frobenius_map_native_batch(fs, power):

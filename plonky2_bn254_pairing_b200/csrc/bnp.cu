@@ -19,6 +19,16 @@
 #include "microcode_tables.h"
 #include "vm.cuh"
 
+// ok[e] = (first ? 1 : ok[e]) & (every limb of element e in the `rows` limb rows of `res` is zero)
+__global__ void bnp_zero_flags_kernel(const u64* res, u32 rows, size_t stride, size_t n, unsigned char* ok, int first) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    u64 acc = 0;
+    for (u32 r = 0; r < rows; r++) acc |= res[(size_t)r * stride + e];
+    const unsigned char z = acc == 0 ? 1 : 0;
+    ok[e] = first ? z : (unsigned char)(ok[e] & z);
+}
+
 namespace {
 
 constexpr unsigned BNP_NCOUNTERS = 1024;  // launches in flight never get near this
@@ -482,6 +492,32 @@ int pow_dev_locked(DevCtx& c, void* stream, const u64* in, u64* out, size_t n, c
     return BNP_OK;
 }
 
+// G1Affine::new / G2Affine::new's acceptance test on device arrays: ok[e] = 1 iff every given point of element e is
+// on its curve and (G2) in the r-torsion subgroup.  g1 / g2 may be NULL (only the other group is checked).
+int validate_dev_locked(DevCtx& c, void* stream, const u64* g1, const u64* g2, unsigned char* ok, size_t n) {
+    if (n == 0) return BNP_OK;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c.stream;
+    int rc;
+    if ((rc = grow(c, st, c.pow_buf[0], c.pow_bytes[0], 6 * 32 * n))) return rc;  // residuals: up to 3 Fq2 per element
+    u64* res = c.pow_buf[0];
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    int first = 1;
+    if (g1) {
+        if ((rc = launch(c, "validate_g1", stream, g1, nullptr, nullptr, nullptr, res, n))) return rc;
+        bnp_zero_flags_kernel<<<blocks, 256, 0, st>>>(res, 2 * 4, n, n, ok, first);
+        CK(cudaGetLastError());
+        first = 0;
+    }
+    if (g2) {
+        if ((rc = launch(c, "validate_g2", stream, nullptr, g2, nullptr, nullptr, res, n))) return rc;
+        bnp_zero_flags_kernel<<<blocks, 256, 0, st>>>(res, 6 * 4, n, n, ok, first);
+        CK(cudaGetLastError());
+        first = 0;
+    }
+    if (first) CK(cudaMemsetAsync(ok, 1, n, st));
+    return BNP_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -608,6 +644,28 @@ int bnp_pow_u64_batch(const uint64_t* in, uint64_t* out, size_t n, const uint64_
     return sync_all();
 }
 
+int bnp_validate_batch(const uint64_t* g1, const uint64_t* g2, unsigned char* ok, size_t n) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ctx.empty()) return BNP_ENODEV;
+    if (n == 0) return BNP_OK;
+    if (!ok) return BNP_EINVAL;
+    auto parts = split_range(n, g_ctx.size());
+    for (size_t d = 0; d < g_ctx.size(); d++) {
+        if (parts[d].cnt == 0) continue;
+        DevCtx& c = g_ctx[d];
+        CK(cudaSetDevice(c.dev));
+        int rc;
+        if (g1 && (rc = copy_in(c, 0, g1, 2, n, parts[d].off, parts[d].cnt))) return rc;
+        if (g2 && (rc = copy_in(c, 1, g2, 4, n, parts[d].off, parts[d].cnt))) return rc;
+        if ((rc = ensure_stage(c, 3, parts[d].cnt))) return rc;
+        unsigned char* flags = reinterpret_cast<unsigned char*>(c.stage[3]);
+        if ((rc = validate_dev_locked(c, nullptr, g1 ? c.stage[0] : nullptr, g2 ? c.stage[1] : nullptr, flags, parts[d].cnt)))
+            return rc;
+        CK(cudaMemcpyAsync(ok + parts[d].off, flags, parts[d].cnt, cudaMemcpyDeviceToHost, c.stream));
+    }
+    return sync_all();
+}
+
 int bnp_fq12_mul_batch(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
     return run_host("fq12_mul", {{2, a, 12}, {4, b, 12}}, out, 12, n);
 }
@@ -716,6 +774,13 @@ int bnp_pow_u64_dev(int device, void* stream, const uint64_t* in, uint64_t* out,
     if (!in || !out || (n_limbs && !exp)) return BNP_EINVAL;
     CK(cudaSetDevice(c->dev));
     return pow_dev_locked(*c, stream, in, out, n, exp, n_limbs);
+}
+
+int bnp_validate_dev(int device, void* stream, const uint64_t* g1, const uint64_t* g2, unsigned char* ok, size_t n) {
+    DEV_PROLOGUE
+    if (!ok) return BNP_EINVAL;
+    CK(cudaSetDevice(c->dev));
+    return validate_dev_locked(*c, stream, g1, g2, ok, n);
 }
 
 int bnp_fq12_mul_dev(int device, void* stream, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {

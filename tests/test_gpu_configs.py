@@ -132,3 +132,58 @@ def test_pow_native_like_the_reference_test(lib, cref):
     assert api.get_naf([O.BN_X]) == O.get_naf([O.BN_X])
     assert [api.frob_coeffs(i) for i in range(4)] == [O.frob_coeffs(i) for i in range(4)]
     assert api.SIX_U_PLUS_2_NAF == O.SIX_U_PLUS_2_NAF and api.BN_X == O.BN_X
+
+
+# ----------------------------------------------------------------------------- on-device input validation
+def _fq2_sqrt(a):
+    """Square root in Fq2 for p = 3 mod 4 (Adj-Rodriguez-Henriquez, eprint 2012/685, algorithm 9), None if a non-residue."""
+    mul, P = O.fq2_mul, O.P
+
+    def pw(x, e):
+        r = (1, 0)
+        while e:
+            if e & 1:
+                r = mul(r, x)
+            x = mul(x, x)
+            e >>= 1
+        return r
+
+    a1 = pw(a, (P - 3) // 4)
+    alpha = mul(a1, mul(a1, a))
+    if mul(pw(alpha, P), alpha) == (P - 1, 0):
+        return None
+    x0 = mul(a1, a)
+    if alpha == (P - 1, 0):
+        return mul((0, 1), x0)
+    return mul(pw(((alpha[0] + 1) % P, alpha[1]), (P - 1) // 2), x0)
+
+
+def test_validate_batch_flags_what_g2affine_new_rejects(lib):
+    """`G2Affine::new` (behind miller_loop_native.rs:303,311) asserts on-curve AND in the r-torsion subgroup."""
+    rnd = random.Random(77)
+    Ps, Qs = wl.point_pool(24)
+    want = [True] * 24
+    Ps, Qs = list(Ps), list(Qs)
+    # off-curve G1 / G2, the (0, 0) encoding of the identity, and points ON the twist but OUTSIDE the subgroup
+    Ps[1] = (Ps[1][0], (Ps[1][1] + 1) % O.P); want[1] = False
+    Qs[2] = (Qs[2][0], ((Qs[2][1][0] + 1) % O.P, Qs[2][1][1])); want[2] = False
+    Ps[3] = (0, 0); want[3] = False
+    Qs[4] = ((0, 0), (0, 0)); want[4] = False
+    b_twist = O.fq2_mul((3, 0), O.fq2_inv((9, 1)))
+    k = 5
+    while k < 12:
+        x = (rnd.randrange(O.P), rnd.randrange(O.P))
+        rhs = O.fq2_mul(O.fq2_mul(x, x), x)
+        rhs = ((rhs[0] + b_twist[0]) % O.P, (rhs[1] + b_twist[1]) % O.P)
+        y = _fq2_sqrt(rhs)
+        if y is None or O.fq2_mul(y, y) != rhs:
+            continue
+        Qs[k] = (x, y)          # on the twist; in the subgroup with probability 1 / (2p - r): never
+        want[k] = False
+        k += 1
+    assert api.validate_batch(Ps, Qs) == want
+    assert api.validate_batch(Ps, None) == [i not in (1, 3) for i in range(24)]
+    assert api.validate_batch(None, Qs) == [i not in (2, 4, 5, 6, 7, 8, 9, 10, 11) for i in range(24)]
+    # a full-size batch of valid points: all ones
+    g1, g2, _ = wl.pairing_inputs(1 << 16, K=K)
+    assert api.validate_soa(g1, g2).all()

@@ -31,9 +31,7 @@ def run(name, arrays, n_slots):
     arrays = dict(arrays)
     arrays[isa.ARR_OUT] = {}
     interp.run(al.words, pool.values, arrays, al.n_slots, al.n_scratch)
-    if len(arrays[isa.ARR_OUT]) > 12:
-        return [arrays[isa.ARR_OUT][i] for i in range(len(arrays[isa.ARR_OUT]))], al
-    return [arrays[isa.ARR_OUT][i] for i in range(12)], al
+    return [arrays[isa.ARR_OUT][i] for i in range(len(arrays[isa.ARR_OUT]))], al
 
 
 PTS = O.seeded_points(0xB2540001, 4)
@@ -209,3 +207,44 @@ def test_phase_split_programs_equal_the_monolithic_program(name, k):
             "final_exp_v0": O.final_exp_native(m)}[name]
     assert got == want
     assert max(works) < 1.25 * sum(works) / k  # balanced: the longest phase bounds the partial last round
+
+
+def test_validation_programs():
+    """SURVEY 8(f).4: the residuals are all zero exactly for points `G1Affine::new` / `G2Affine::new` accept."""
+    p, q = PTS[0]
+    got, _ = run("validate_g1", {isa.ARR_G1: [p[0], p[1]]}, 9)
+    assert got[:2] == [0, 0]
+    got, _ = run("validate_g1", {isa.ARR_G1: [p[0], (p[1] + 5) % O.P]}, 9)
+    assert got[0] != 0 and got[1] != 0
+    flat = [q[0][0], q[0][1], q[1][0], q[1][1]]
+    got, al = run("validate_g2", {isa.ARR_G2: flat}, 9)
+    assert got[:6] == [0] * 6
+    bad = list(flat)
+    bad[3] = (bad[3] + 1) % O.P
+    got, _ = run("validate_g2", {isa.ARR_G2: bad}, 9)
+    assert any(got[:2]) and any(got[2:6])
+    # 3 * Q' for a point Q' of the twist outside the subgroup: cofactor-cleared points pass, Q' itself fails
+    # (Q' = a fixed on-twist point found by solving y^2 = x^3 + 3/(9+u) for x = (1, 0) ... (5, 0))
+    b_tw = O.fq2_mul((3, 0), O.fq2_inv((9, 1)))
+    for x0 in range(1, 40):
+        x = (x0, 0)
+        rhs = O.fq2_mul(O.fq2_mul(x, x), x)
+        rhs = ((rhs[0] + b_tw[0]) % O.P, (rhs[1] + b_tw[1]) % O.P)
+        # Fq2 square root by the norm trick (p = 3 mod 4)
+        n = (rhs[0] * rhs[0] + rhs[1] * rhs[1]) % O.P
+        s = pow(n, (O.P + 1) // 4, O.P)
+        if s * s % O.P != n:
+            continue
+        for sgn in (1, -1):
+            t = (rhs[0] + sgn * s) * pow(2, O.P - 2, O.P) % O.P
+            c = pow(t, (O.P + 1) // 4, O.P)
+            if c * c % O.P == t and c:
+                y = (c, rhs[1] * pow(2 * c, O.P - 2, O.P) % O.P)
+                if O.fq2_mul(y, y) == rhs:
+                    got, _ = run("validate_g2", {isa.ARR_G2: [x[0], x[1], y[0], y[1]]}, 9)
+                    assert got[:2] == [0, 0] and any(got[2:6])   # on the twist, not in the subgroup
+                    cleared = O.g2_mul((x, y), 2 * O.P - O.R_ORDER)   # times the cofactor: now in the subgroup
+                    got, _ = run("validate_g2", {isa.ARR_G2: [cleared[0][0], cleared[0][1], cleared[1][0], cleared[1][1]]}, 9)
+                    assert got[:6] == [0] * 6
+                    return
+    raise AssertionError("no twist point found")
