@@ -127,7 +127,8 @@ int bnp_imad32_peak(int device, double* imads_per_s);
 /* Run an arbitrary sequencer program by name on device arrays (test hook for op-level parity). */
 int bnp_run_program_dev(int device, void* stream, const char* program, const uint64_t* g1, const uint64_t* g2,
                         const uint64_t* f12, const uint64_t* aux, uint64_t* out, size_t n);
-/* Tuning knobs (0 keeps the current setting): threads per block (32/64/128/256; one thread per pairing), and whether
+/* Tuning knobs (0 keeps the current setting): threads per block (32/64/128/256/384/512; one thread per pairing; default 384 =
+ * one block per SM, whose shared memory plus tensor memory hold 18 Fq2 slots per pairing), and whether
  * programs are run as
  * phase-split task queues (1 = automatic: when the unsplit batch would leave the last round of warp-tasks badly
  * filled, 2 = never, 3 = whenever the library has a split variant of the program). */

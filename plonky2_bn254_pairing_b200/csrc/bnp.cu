@@ -61,7 +61,7 @@ std::mutex g_mu;
 std::mutex g_launch_mu;  // serialises launch() between the per-device worker threads of one host-pointer call
 std::vector<DevCtx> g_ctx;
 std::atomic<uint64_t> g_launches{0};
-int g_threads_per_block = 64;  // blocks of 64 threads: one thread per pairing
+int g_threads_per_block = 384;  // one thread per pairing; 12 warps = one block per SM, 3 warps per TMEM lane quarter
 thread_local std::string g_last_error;
 
 int cuda_fail(cudaError_t e, const char* what) {
@@ -129,20 +129,47 @@ int launch_T(DevCtx& c, const BnpProgram& p, int pidx, cudaStream_t st, u64* con
         scratch = std::max(scratch, q.n_scratch);
         n_state = std::max(n_state, q.n_state);
     }
-    // a thread holds the 64-byte Fq2 value of every slot; BNP_SMEM_PAD (experiments only) lowers the occupancy
+    // A thread holds the 64-byte Fq2 value of every slot, half of it (limbs 0-3 of both components) in shared memory and
+    // half in tensor memory, 8 columns per slot (vm.cuh, Slots).  The warps of a block that share a TMEM lane quarter
+    // (warp % 4) take consecutive column ranges; an allocation is a power of two >= 32 columns out of 512 per SM.
     static const size_t pad = std::getenv("BNP_SMEM_PAD") ? (size_t)std::atol(std::getenv("BNP_SMEM_PAD")) : 0;
-    const size_t smem = (size_t)slots * 64 * T + pad;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < slots * 8u * ((T / 32 + 3) / 4)) tmem_cols *= 2;
+    if (tmem_cols > 512) {
+        g_last_error = "program needs more tensor-memory columns than a block of this size can have";
+        return BNP_EUNSUPPORTED;
+    }
+    size_t smem = (size_t)slots * 32 * T + pad;
     // the attribute and the occupancy of a (device, block size, shared memory) triple never change: ask once
-    static std::map<std::tuple<int, int, size_t>, int> occ_cache;
+    static std::map<std::tuple<int, int, size_t, uint32_t>, std::pair<int, size_t>> occ_cache;
     int per_sm = 0;
-    auto key = std::make_tuple(c.dev, T, smem);
+    auto key = std::make_tuple(c.dev, T, smem, tmem_cols);
     auto hit = occ_cache.find(key);
     if (hit != occ_cache.end()) {
-        per_sm = hit->second;
+        per_sm = hit->second.first;
+        smem = hit->second.second;
     } else {
+        int optin = 0;
+        CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.dev));
+        if (smem > (size_t)optin) {
+            g_last_error = "program does not fit in shared memory at this block size";
+            return BNP_EUNSUPPORTED;
+        }
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
-        occ_cache[key] = per_sm;
+        if (per_sm > (int)(512 / tmem_cols)) {
+            // more blocks would fit than tensor memory has columns for: a block that cannot allocate would sit in
+            // tcgen05.alloc until another one exits.  Ask for enough shared memory to make the limits agree.
+            const int want = (int)(512 / tmem_cols);
+            int dev_smem = 0;
+            CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c.dev));
+            const size_t padded = (size_t)dev_smem / (size_t)(want + 1) + 1;
+            smem = std::min(std::max(smem, padded), (size_t)optin);
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem));
+            per_sm = std::min(per_sm, want);
+        }
+        occ_cache[key] = std::make_pair(per_sm, smem);
     }
     if (per_sm < 1) {
         g_last_error = "program does not fit in shared memory";
@@ -183,6 +210,8 @@ int launch_T(DevCtx& c, const BnpProgram& p, int pidx, cudaStream_t st, u64* con
         a.arr[BNP_NARR - 1] = c.state;
     }
     a.scratch = c.scratch;
+    a.tmem_cols = tmem_cols;
+    a.tmem_cols_per_warp = slots * 8u;
     a.n = (u32)n;
     a.stride = (u32)stride;
     a.counter = c.counters + (c.next_counter++ % BNP_NCOUNTERS);
@@ -217,6 +246,8 @@ int launch(DevCtx& c, const char* prog, void* stream, const u64* g1, const u64* 
         case 32: return launch_T<32>(c, *p, pidx, st, arr, n, stride);
         case 128: return launch_T<128>(c, *p, pidx, st, arr, n, stride);
         case 256: return launch_T<256>(c, *p, pidx, st, arr, n, stride);
+        case 384: return launch_T<384>(c, *p, pidx, st, arr, n, stride);
+        case 512: return launch_T<512>(c, *p, pidx, st, arr, n, stride);
         default: return launch_T<64>(c, *p, pidx, st, arr, n, stride);
     }
 }
@@ -817,7 +848,8 @@ int bnp_set_launch_config(int threads_per_block, int phase_mode) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (phase_mode >= 1 && phase_mode <= 3) g_phase_mode = phase_mode - 2;  // 1 automatic, 2 never split, 3 always split
     if (threads_per_block == 0) return BNP_OK;
-    if (threads_per_block != 32 && threads_per_block != 64 && threads_per_block != 128 && threads_per_block != 256)
+    if (threads_per_block != 32 && threads_per_block != 64 && threads_per_block != 128 && threads_per_block != 256 &&
+        threads_per_block != 384 && threads_per_block != 512)
         return BNP_EINVAL;
     g_threads_per_block = threads_per_block;
     return BNP_OK;

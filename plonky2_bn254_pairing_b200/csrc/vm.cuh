@@ -36,38 +36,98 @@ struct VmArgs {
     u32* counter;           // work counter (zeroed before launch): warps claim (phase, 32-element chunk) tasks
     u32* progress;          // per chunk: number of completed phases (zeroed before launch; unused when n_phases == 1)
     u32 n_phases;
+    u32 tmem_cols;          // TMEM columns this block allocates (a power of two >= 32)
+    u32 tmem_cols_per_warp; // 8 * number of slots: the column range of one warp
 };
 
 __device__ __constant__ u32 BNP_CONSTS[BNP_MAX_CONST][16];
 
-// Shared-memory slots: [slot][quad][thread] uint4; quads 0,1 = c0, quads 2,3 = c1.
-// (Measured and dropped in round 2: "memory operands" - slot fields that name a scratch entry in global memory, so
-// that a value read once is not FILLed into a slot first.  The programs shrank from 18.4 k to 12.9 k instructions per
-// pairing, but a second access path at every operand site - by a uniform branch or by generic addressing - cost the
-// kernel 10 % before a single memory operand was used: 2.15-2.20 M pairings/s against 2.40 M.)
+// The slot file: every 64-byte Fq2 slot is SPLIT between shared memory and TENSOR MEMORY.
+//
+// This kernel issues no tcgen05.mma, so the SM's 256 KB of TMEM would sit idle while shared memory - the only other
+// indexable on-chip store - caps the kernel at 9 slots per pairing and makes every second sequencer instruction a
+// spill or a re-load.  tcgen05.ld / tcgen05.st in the 32x32b shape give every thread of a warp its own TMEM lane and
+// N consecutive 32-bit columns per access, addressed by a register: a per-thread indexable scratchpad.  A warp reaches
+// the lane quarter 32 * (warp % 4); the warps of a block that share a quarter take consecutive column ranges.
+//
+// Layout: limbs 0-3 of both components live in shared memory, [slot][component][thread] as uint4 (conflict-free
+// LDS.128 / STS.128), limbs 4-7 in tensor memory, 8 columns per slot (c0 limbs 4-7, then c1 limbs 4-7).  Every access
+// is the same straight-line pair of instructions - no second access path, no branch, no flag (measured first: slots
+// living EITHER in shared memory OR in tensor memory, picked by a compare per access, cost 70 cycles of branch latency
+// per access, 8 % of the kernel; profiles/experiments_r2.txt).  One 384-thread block per SM then holds 18 slots per
+// pairing instead of 9, and a fused pairing shrinks from 18 400 to 9 300 sequencer instructions (spills and re-loads
+// from 9 600 to 1 000); a 512-thread block holds 14 slots at 16 warps per SM.
+#ifndef BNP_ST_WAIT_LATE
+#define BNP_ST_WAIT_LATE 0
+#endif
+#if BNP_ST_WAIT_LATE   // experiment: wait for outstanding TMEM stores in front of the next TMEM load instead of behind the store
+#define BNP_ST_WAIT_PREFIX "tcgen05.wait::st.sync.aligned;\n\t"
+#define BNP_ST_WAIT_SUFFIX ""
+#else
+#define BNP_ST_WAIT_PREFIX ""
+#define BNP_ST_WAIT_SUFFIX "\n\ttcgen05.wait::st.sync.aligned;"
+#endif
 template <int T>
 struct Slots {
-    uint4* base;  // already offset by threadIdx.x
+    uint4* base;  // shared memory: this thread's entry of slot 0, component 0
+    u32 tbase;    // tensor memory: this warp's lane quarter, first column of its range (slot s: tbase + 8 s)
+
+    // A load is ISSUED (both halves in flight) and later WAITED for, so that the operands of one instruction share one
+    // tcgen05.wait::ld.  `wait*` carries the real wait instruction for every TMEM load issued so far; `dep*` emits
+    // nothing and only ties further registers to the statement order (volatile statements keep their order), so that
+    // no use of them is scheduled before the wait.
+    __device__ __forceinline__ void issue_half(u32* r, u32 s, u32 half) const {
+        const uint4 q = base[s * (2 * T) + half * T];
+        r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w;
+        asm volatile(BNP_ST_WAIT_PREFIX "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(tbase + s * 8u + half * 4u));
+    }
+    __device__ __forceinline__ void issue(Fp2& r, u32 s) const {
+        const uint4* p = base + s * (2 * T);
+        const uint4 q0 = p[0], q1 = p[T];
+        r.c0[0] = q0.x; r.c0[1] = q0.y; r.c0[2] = q0.z; r.c0[3] = q0.w;
+        r.c1[0] = q1.x; r.c1[1] = q1.y; r.c1[2] = q1.z; r.c1[3] = q1.w;
+        asm volatile(BNP_ST_WAIT_PREFIX "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r.c0[4]), "=r"(r.c0[5]), "=r"(r.c0[6]), "=r"(r.c0[7]), "=r"(r.c1[4]), "=r"(r.c1[5]),
+                       "=r"(r.c1[6]), "=r"(r.c1[7])
+                     : "r"(tbase + s * 8u));
+    }
+    __device__ __forceinline__ static void wait_half(u32* r) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]));
+    }
+    __device__ __forceinline__ static void dep_half(u32* r) {
+        asm volatile("" : "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]));
+    }
+    __device__ __forceinline__ static void wait(Fp2& r) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+r"(r.c0[4]), "+r"(r.c0[5]), "+r"(r.c0[6]), "+r"(r.c0[7]), "+r"(r.c1[4]), "+r"(r.c1[5]),
+                       "+r"(r.c1[6]), "+r"(r.c1[7]));
+    }
+    __device__ __forceinline__ static void dep(Fp2& r) {
+        asm volatile(""
+                     : "+r"(r.c0[4]), "+r"(r.c0[5]), "+r"(r.c0[6]), "+r"(r.c0[7]), "+r"(r.c1[4]), "+r"(r.c1[5]),
+                       "+r"(r.c1[6]), "+r"(r.c1[7]));
+    }
     __device__ __forceinline__ void load_half(u32* r, u32 s, u32 half) const {
-        const uint4* p = base + s * (4 * T) + half * (2 * T);
-        uint4 q0 = p[0], q1 = p[T];
-        r[0] = q0.x; r[1] = q0.y; r[2] = q0.z; r[3] = q0.w;
-        r[4] = q1.x; r[5] = q1.y; r[6] = q1.z; r[7] = q1.w;
+        issue_half(r, s, half);
+        wait_half(r);
     }
     __device__ __forceinline__ void load(Fp2& r, u32 s) const {
-        const uint4* p = base + s * (4 * T);
-        uint4 q0 = p[0], q1 = p[T], q2 = p[2 * T], q3 = p[3 * T];
-        r.c0[0] = q0.x; r.c0[1] = q0.y; r.c0[2] = q0.z; r.c0[3] = q0.w;
-        r.c0[4] = q1.x; r.c0[5] = q1.y; r.c0[6] = q1.z; r.c0[7] = q1.w;
-        r.c1[0] = q2.x; r.c1[1] = q2.y; r.c1[2] = q2.z; r.c1[3] = q2.w;
-        r.c1[4] = q3.x; r.c1[5] = q3.y; r.c1[6] = q3.z; r.c1[7] = q3.w;
+        issue(r, s);
+        wait(r);
     }
+    // (the asm statements are volatile: a load of a slot is never moved across a store)
     __device__ __forceinline__ void store(u32 s, const Fp2& r) const {
-        uint4* p = base + s * (4 * T);
+        uint4* p = base + s * (2 * T);
         p[0] = make_uint4(r.c0[0], r.c0[1], r.c0[2], r.c0[3]);
-        p[T] = make_uint4(r.c0[4], r.c0[5], r.c0[6], r.c0[7]);
-        p[2 * T] = make_uint4(r.c1[0], r.c1[1], r.c1[2], r.c1[3]);
-        p[3 * T] = make_uint4(r.c1[4], r.c1[5], r.c1[6], r.c1[7]);
+        p[T] = make_uint4(r.c1[0], r.c1[1], r.c1[2], r.c1[3]);
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};" BNP_ST_WAIT_SUFFIX
+            :
+            : "r"(r.c0[4]), "r"(r.c0[5]), "r"(r.c0[6]), "r"(r.c0[7]), "r"(r.c1[4]), "r"(r.c1[5]), "r"(r.c1[6]),
+              "r"(r.c1[7]), "r"(tbase + s * 8u)
+            : "memory");
     }
 };
 
@@ -99,8 +159,10 @@ __device__ __forceinline__ void stg_fp(u64* arr, u32 f, u32 n, u32 e, const u32*
 #define BNP_LIN_FETCH(J, ZA, ZB, TT)                                          \
     {                                                                         \
         TT = __ldg(ents + (J));                                               \
-        S.load_half(ZA, TT & 0xffu, (TT >> 8) & 1u);                          \
-        S.load_half(ZB, (TT >> 16) & 0xffu, (TT >> 24) & 1u);                 \
+        S.issue_half(ZA, TT & 0xffu, (TT >> 8) & 1u);                         \
+        S.issue_half(ZB, (TT >> 16) & 0xffu, (TT >> 24) & 1u);                \
+        S.wait_half(ZA);                                                      \
+        S.dep_half(ZB);                                                       \
     }
 #define BNP_LIN_ACC(ZA, ZB, TT)                                               \
     {                                                                         \
@@ -155,21 +217,6 @@ template <int T>
 __device__ __forceinline__ void vm_lin(const Slots<T>& S, Fp2& out, u32 n, const u64* more) {
     const u32* ents = (const u32*)more;  // pair j is the j-th 32-bit word of the entry list
     u64 E0[5], O0[5], E1[5], O1[5];
-#ifdef BNP_LIN_PIPELINED
-    // hand-pipelined form (three copies of the entry body: +3 KB of hot code)
-    u32 za[8], zb[8], ya[8], yb[8], ta, ua;
-    BNP_LIN_FETCH(0u, za, zb, ta);
-    if (1u < n) BNP_LIN_FETCH(1u, ya, yb, ua);
-    BNP_LIN_ACC_FIRST(za, zb, ta);
-#pragma unroll 1
-    for (u32 j = 1; j < n; j += 2u) {   // (ya, yb) hold pair j
-        if (j + 1u < n) BNP_LIN_FETCH(j + 1u, za, zb, ta);
-        BNP_LIN_ACC(ya, yb, ua);
-        if (j + 1u >= n) break;
-        if (j + 2u < n) BNP_LIN_FETCH(j + 2u, ya, yb, ua);
-        BNP_LIN_ACC(za, zb, ta);
-    }
-#else
 #pragma unroll
     for (int i = 0; i < 5; i++) E0[i] = O0[i] = E1[i] = O1[i] = 0ull;
 #pragma unroll 1
@@ -178,7 +225,6 @@ __device__ __forceinline__ void vm_lin(const Slots<T>& S, Fp2& out, u32 n, const
         BNP_LIN_FETCH(j, za, zb, ta);
         BNP_LIN_ACC(za, zb, ta);
     }
-#endif
     u32 v0[9], v1[9];
     lin_merge(v0, E0, O0);
     lin_merge(v1, E1, O1);
@@ -192,6 +238,31 @@ __device__ __forceinline__ void vm_lin(const Slots<T>& S, Fp2& out, u32 n, const
 // On entry `pc` points at the word after the instruction; on exit `ins` holds the next instruction
 // and `pc` points past it.
 // ---------------------------------------------------------------------------------------------
+// raw operand fetch of a product-class instruction (no arithmetic): x = S[a]; y = S[c] (MUL) or the Fq half of
+// S[b] (MULFP, into y.c0); tb = S[b], te = S[e] when the pre-addition flags ask for them
+template <int T>
+__device__ __forceinline__ void vm_product_fetch(const Slots<T>& S, u32 op, u32 a, u32 b, u32 c, u32 ee, u32 imm, Fp2& x,
+                                                 Fp2& y, Fp2& tb, Fp2& te) {
+    S.issue(x, a);
+    if (op == BNP_OP_MUL) {
+        S.issue(y, c);
+        if (imm & BNP_MUL_B) S.issue(tb, b);
+        if (imm & BNP_MUL_E) S.issue(te, ee);
+        S.wait(x);
+        S.dep(y);
+        if (imm & BNP_MUL_B) S.dep(tb);
+        if (imm & BNP_MUL_E) S.dep(te);
+    } else if (op == BNP_OP_SQR) {
+        if (imm & BNP_MUL_B) S.issue(tb, b);
+        S.wait(x);
+        if (imm & BNP_MUL_B) S.dep(tb);
+    } else {
+        S.issue_half(y.c0, b, (imm & BNP_MULFP_HALF) ? 1u : 0u);
+        S.wait(x);
+        S.dep_half(y.c0);
+    }
+}
+
 template <int T>
 __device__ __forceinline__ void vm_product(const Slots<T>& S, u32 op, const u64*& pc, u64& ins, const u64 w0, u32 d, u32 a,
                                            u32 b, u32 c, u32 ee, u32 imm) {
@@ -204,23 +275,19 @@ __device__ __forceinline__ void vm_product(const Slots<T>& S, u32 op, const u64*
     //   MULFP:  T0 = x0 s, T1 = x1 s
     u32 T0[16], T1[16];
     u32 u0[8], v0[8], u1[8], v1[8], sx[8], sy[8];
+    Fp2 x, y, tb, te;
+    vm_product_fetch<T>(S, op, a, b, c, ee, imm, x, y, tb, te);
     if (op == BNP_OP_MUL) {
-        Fp2 x, y;
-        S.load(x, a);
-        S.load(y, c);
-        if (imm & (BNP_MUL_B | BNP_MUL_E)) {  // Karatsuba-level operands: (a +- b) * (c +- e), sums kept lazy (< 2p)
-            Fp2 t;
+        if (op == BNP_OP_MUL && (imm & (BNP_MUL_B | BNP_MUL_E))) {  // Karatsuba-level operands: (a +- b) * (c +- e), sums kept lazy (< 2p)
             if (imm & BNP_MUL_B) {
-                S.load(t, b);
-                if (imm & BNP_MUL_BNEG) fp2_sub_lazy(x, x, t); else fp2_add_lazy(x, x, t);
+                if (imm & BNP_MUL_BNEG) fp2_sub_lazy(x, x, tb); else fp2_add_lazy(x, x, tb);
                 if (imm & BNP_MUL_BCANON) {
                     fp_cond_sub_p(x.c0);
                     fp_cond_sub_p(x.c1);
                 }
             }
             if (imm & BNP_MUL_E) {
-                S.load(t, ee);
-                if (imm & BNP_MUL_ENEG) fp2_sub_lazy(y, y, t); else fp2_add_lazy(y, y, t);
+                if (imm & BNP_MUL_ENEG) fp2_sub_lazy(y, y, te); else fp2_add_lazy(y, y, te);
             }
         }
         add8(sx, x.c0, x.c1);  // < 4p < 2^256
@@ -228,12 +295,8 @@ __device__ __forceinline__ void vm_product(const Slots<T>& S, u32 op, const u64*
 #pragma unroll
         for (int i = 0; i < 8; i++) { u0[i] = x.c0[i]; v0[i] = y.c0[i]; u1[i] = x.c1[i]; v1[i] = y.c1[i]; }
     } else if (op == BNP_OP_SQR) {
-        Fp2 x;
-        S.load(x, a);
         if (imm & BNP_MUL_B) {
-            Fp2 t;
-            S.load(t, b);
-            if (imm & BNP_MUL_BNEG) fp2_sub(x, x, t); else fp2_add(x, x, t);
+            if (imm & BNP_MUL_BNEG) fp2_sub(x, x, tb); else fp2_add(x, x, tb);
         }
         add8(u0, x.c0, x.c1);
         fp_sub(v0, x.c0, x.c1);
@@ -241,11 +304,8 @@ __device__ __forceinline__ void vm_product(const Slots<T>& S, u32 op, const u64*
 #pragma unroll
         for (int i = 0; i < 8; i++) { v1[i] = x.c1[i]; sx[i] = sy[i] = 0u; }
     } else {
-        Fp2 x;
-        S.load(x, a);
-        S.load_half(v0, b, (imm & BNP_MULFP_HALF) ? 1u : 0u);
 #pragma unroll
-        for (int i = 0; i < 8; i++) { u0[i] = x.c0[i]; u1[i] = x.c1[i]; v1[i] = v0[i]; sx[i] = sy[i] = 0u; }
+        for (int i = 0; i < 8; i++) { u0[i] = x.c0[i]; u1[i] = x.c1[i]; v0[i] = v1[i] = y.c0[i]; sx[i] = sy[i] = 0u; }
     }
     fp_mul_wide(T0, u0, v0);
     fp_mul_wide(T1, u1, v1);
@@ -317,11 +377,28 @@ __device__ __forceinline__ void vm_product(const Slots<T>& S, u32 op, const u64*
 #endif
 
 template <int T>
-__global__ void __launch_bounds__(T, (BNP_MINB * 64) / T) bnp_vm_kernel(VmArgs args) {
+__global__ void __launch_bounds__(T, (BNP_MINB * 64) / T > 0 ? (BNP_MINB * 64) / T : 1) bnp_vm_kernel(VmArgs args) {
     extern __shared__ uint4 bnp_smem[];
+    __shared__ u32 tmem_base;
     const u32 lane = threadIdx.x & 31u;
     Slots<T> S;
     S.base = bnp_smem + threadIdx.x;
+    // Tensor memory: warp 0 allocates the block's columns, every warp derives the address of its own lane quarter and
+    // column range.
+    if (threadIdx.x < 32u) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         (u32)__cvta_generic_to_shared(&tmem_base)),
+                     "r"(args.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+        const u32 warp = threadIdx.x >> 5;
+        S.tbase = tmem_base + (((warp & 3u) * 32u) << 16) + (warp >> 2) * args.tmem_cols_per_warp;
+    }
     const u32 total = gridDim.x * T;
     const u32 gtid = blockIdx.x * T + threadIdx.x;
     uint4* scr = args.scratch + gtid;
@@ -416,26 +493,26 @@ __global__ void __launch_bounds__(T, (BNP_MINB * 64) / T) bnp_vm_kernel(VmArgs a
                     pc++;
                     break;
                 case BNP_OP_SPILL: {
-                    const uint4* p = S.base + a * (4 * T);
+                    S.load(x, a);
                     uint4* q = scr + (size_t)imm * 4 * total;
-                    q[0] = p[0];
-                    q[total] = p[T];
-                    q[2 * (size_t)total] = p[2 * T];
-                    q[3 * (size_t)total] = p[3 * T];
+                    q[0] = make_uint4(x.c0[0], x.c0[1], x.c0[2], x.c0[3]);
+                    q[total] = make_uint4(x.c0[4], x.c0[5], x.c0[6], x.c0[7]);
+                    q[2 * (size_t)total] = make_uint4(x.c1[0], x.c1[1], x.c1[2], x.c1[3]);
+                    q[3 * (size_t)total] = make_uint4(x.c1[4], x.c1[5], x.c1[6], x.c1[7]);
                     ins = w0;
                     pc++;
                     break;
                 }
                 case BNP_OP_FILL: {
-                    uint4* p = S.base + d * (4 * T);
                     const uint4* q = scr + (size_t)imm * 4 * total;
                     // read-once data: bypass L1 (what little L1 the slots leave holds the instruction words)
                     const uint4 q0 = __ldcg(q), q1 = __ldcg(q + total), q2 = __ldcg(q + 2 * (size_t)total),
                                 q3 = __ldcg(q + 3 * (size_t)total);
-                    p[0] = q0;
-                    p[T] = q1;
-                    p[2 * T] = q2;
-                    p[3 * T] = q3;
+                    r.c0[0] = q0.x; r.c0[1] = q0.y; r.c0[2] = q0.z; r.c0[3] = q0.w;
+                    r.c0[4] = q1.x; r.c0[5] = q1.y; r.c0[6] = q1.z; r.c0[7] = q1.w;
+                    r.c1[0] = q2.x; r.c1[1] = q2.y; r.c1[2] = q2.z; r.c1[3] = q2.w;
+                    r.c1[4] = q3.x; r.c1[5] = q3.y; r.c1[6] = q3.z; r.c1[7] = q3.w;
+                    S.store(d, r);
                     ins = w0;
                     pc++;
                     break;
@@ -504,6 +581,10 @@ __global__ void __launch_bounds__(T, (BNP_MINB * 64) / T) bnp_vm_kernel(VmArgs a
                 asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(args.progress + chunk), "r"(phase + 1u) : "memory");
         }
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32u)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(args.tmem_cols) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------

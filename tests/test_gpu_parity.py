@@ -150,7 +150,7 @@ def test_every_launch_configuration_bit_exact(lib, cref, threads, phase_mode):
         got = api.pairing_soa(g1, g2)
         got_m = api.miller_loop_soa(g1, g2)
     finally:
-        assert lib.bnp_set_launch_config(64, 1) == 0
+        assert lib.bnp_set_launch_config(384, 1) == 0
     assert np.array_equal(got, cref.pairing(g1, g2))
     assert np.array_equal(got_m, cref.miller(g1, g2))
 

@@ -13,7 +13,7 @@ def run(name, arrays, n_slots):
     pool = ConstPool()
     b = programs.build_program(name, pool)
     from plonky2_bn254_pairing_b200.microcode import fuse
-    al = alloc.allocate(fuse.fuse(b.ops), n_slots)
+    al = alloc.allocate(fuse.fuse(b.ops, max_srcs=min(fuse.MAX_SRCS, n_slots - 2)), n_slots)   # gen.build_all's rule
     for ins in isa.parse(al.words):  # every operand field within the slot budget
         for sl in ins.slots_read() + ins.slots_written():
             assert sl < n_slots, ins.op

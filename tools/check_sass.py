@@ -16,9 +16,9 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KERNEL = "bnp_vm_kernelILi64E"
+KERNEL = "bnp_vm_kernelILi384E"
 MAX_REGS = 170
-MAX_INSTRS = 4096
+MAX_INSTRS = 4608
 MAX_IMAD_HI = 8 * 10   # reduction instances: 2 in the product tail, the rest in the inversion / LIN / MULXI helpers
 
 
