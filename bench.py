@@ -575,7 +575,7 @@ def run_gpu(args):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         alg_bytes = n * (k * 192 + 384) if args.workload != "final_exp" else n * 768
-        threads = env_int("BNP_THREADS", 64) or 64
+        threads = lib.bnp_threads_per_block()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

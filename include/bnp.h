@@ -133,6 +133,8 @@ int bnp_run_program_dev(int device, void* stream, const char* program, const uin
  * phase-split task queues (1 = automatic: when the unsplit batch would leave the last round of warp-tasks badly
  * filled, 2 = never, 3 = whenever the library has a split variant of the program). */
 int bnp_set_launch_config(int threads_per_block, int phase_mode);
+/* Threads per block the sequencer kernel is launched with (bench.py reports the kernel instance it timed). */
+int bnp_threads_per_block(void);
 
 #ifdef __cplusplus
 }

@@ -110,25 +110,26 @@ template <int T>
 int launch_T(DevCtx& c, const BnpProgram& p, int pidx, cudaStream_t st, u64* const arr[BNP_NARR], size_t n,
              size_t stride) {
     auto kern = bnp_vm_kernel<T>;
-    // phase-split variant "name#K.i" (microcode/phases.py), if the library has one
-    int ph_idx[BNP_MAX_PHASES];
-    int n_ph = 0;
-    for (int K = BNP_MAX_PHASES; K >= 2 && n_ph == 0; K--) {
+    // phase-split variants "name#K.i" (microcode/phases.py): the library holds a few phase counts K per program
+    int var_idx[BNP_MAX_PHASES + 1][BNP_MAX_PHASES];
+    std::vector<int> var_K;
+    for (int K = 2; K <= BNP_MAX_PHASES; K++) {
         int got = 0;
         for (int i = 0; i < K; i++) {
             std::string nm = std::string(p.name) + "#" + std::to_string(K) + "." + std::to_string(i);
-            if (!find_program(nm.c_str(), &ph_idx[i])) break;
+            if (!find_program(nm.c_str(), &var_idx[K][i])) break;
             got++;
         }
-        if (got == K) n_ph = K;
+        if (got == K) var_K.push_back(K);
     }
     uint32_t slots = p.n_slots, scratch = p.n_scratch, n_state = 0;
-    for (int i = 0; i < n_ph; i++) {
-        const BnpProgram& q = BNP_PROGRAMS[ph_idx[i]];
-        slots = std::max(slots, q.n_slots);
-        scratch = std::max(scratch, q.n_scratch);
-        n_state = std::max(n_state, q.n_state);
-    }
+    for (int K : var_K)
+        for (int i = 0; i < K; i++) {
+            const BnpProgram& q = BNP_PROGRAMS[var_idx[K][i]];
+            slots = std::max(slots, q.n_slots);
+            scratch = std::max(scratch, q.n_scratch);
+            n_state = std::max(n_state, q.n_state);
+        }
     // A thread holds the 64-byte Fq2 value of every slot, half of it (limbs 0-3 of both components) in shared memory and
     // half in tensor memory, 8 columns per slot (vm.cuh, Slots).  The warps of a block that share a TMEM lane quarter
     // (warp % 4) take consecutive column ranges; an allocation is a power of two >= 32 columns out of 512 per SM.
@@ -177,13 +178,25 @@ int launch_T(DevCtx& c, const BnpProgram& p, int pidx, cudaStream_t st, u64* con
     }
     const size_t n_chunks = (n + BNP_CHUNK - 1) / BNP_CHUNK;  // a warp works on 32 pairings, one per lane
     const size_t resident_warps = (size_t)per_sm * c.sm_count * (T / 32);
-    // Split when the unsplit batch would leave the last round of warp-tasks badly filled.
+    // Tasks are (phase, chunk) pairs of equal length handed out breadth-first, so a launch takes ceil(tasks / warps)
+    // task times: split when the unsplit batch would leave the last round badly filled, with the phase count whose
+    // last round is fullest (2^16 pairings on 148 x 12 warps: 13 phases make 14.99 rounds, 16 make 18.45 - 3 % idle).
     bool split = false;
-    if (n_ph) {
+    int n_ph = 0;
+    const int* ph_idx = nullptr;
+    if (!var_K.empty()) {
         const double rounds = (double)n_chunks / (double)resident_warps;
         const double loss1 = std::ceil(rounds) / rounds - 1.0;
-        const double lossK = std::ceil(rounds * n_ph) / (rounds * n_ph) - 1.0;
-        split = rounds > 1.0 && loss1 > 0.04 && lossK < loss1;
+        double best = 1e9;
+        for (int K : var_K) {
+            const double lossK = std::ceil(rounds * K) / (rounds * K) - 1.0;
+            if (lossK <= best) {   // ties: the finer split
+                best = lossK;
+                n_ph = K;
+            }
+        }
+        ph_idx = var_idx[n_ph];
+        split = rounds > 1.0 && loss1 > 0.04 && best < loss1;
         if (g_phase_mode == 0) split = false;
         if (g_phase_mode == 1) split = true;
     }
@@ -247,6 +260,7 @@ int launch(DevCtx& c, const char* prog, void* stream, const u64* g1, const u64* 
         case 128: return launch_T<128>(c, *p, pidx, st, arr, n, stride);
         case 256: return launch_T<256>(c, *p, pidx, st, arr, n, stride);
         case 384: return launch_T<384>(c, *p, pidx, st, arr, n, stride);
+        case 448: return launch_T<448>(c, *p, pidx, st, arr, n, stride);
         case 512: return launch_T<512>(c, *p, pidx, st, arr, n, stride);
         default: return launch_T<64>(c, *p, pidx, st, arr, n, stride);
     }
@@ -849,11 +863,13 @@ int bnp_set_launch_config(int threads_per_block, int phase_mode) {
     if (phase_mode >= 1 && phase_mode <= 3) g_phase_mode = phase_mode - 2;  // 1 automatic, 2 never split, 3 always split
     if (threads_per_block == 0) return BNP_OK;
     if (threads_per_block != 32 && threads_per_block != 64 && threads_per_block != 128 && threads_per_block != 256 &&
-        threads_per_block != 384 && threads_per_block != 512)
+        threads_per_block != 384 && threads_per_block != 448 && threads_per_block != 512)
         return BNP_EINVAL;
     g_threads_per_block = threads_per_block;
     return BNP_OK;
 }
+
+int bnp_threads_per_block(void) { return g_threads_per_block; }
 
 static int imad_peak_impl(DevCtx* c, int wide, double* per_s) {
     CK(cudaSetDevice(c->dev));

@@ -377,7 +377,11 @@ __device__ __forceinline__ void vm_product(const Slots<T>& S, u32 op, const u64*
 #endif
 
 template <int T>
+#ifdef BNP_MAXNREG   // experiments: an explicit register cap instead of the launch bounds
+__global__ void __maxnreg__(BNP_MAXNREG) bnp_vm_kernel(VmArgs args) {
+#else
 __global__ void __launch_bounds__(T, (BNP_MINB * 64) / T > 0 ? (BNP_MINB * 64) / T : 1) bnp_vm_kernel(VmArgs args) {
+#endif
     extern __shared__ uint4 bnp_smem[];
     __shared__ u32 tmem_base;
     const u32 lane = threadIdx.x & 31u;

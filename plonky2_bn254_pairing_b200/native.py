@@ -48,6 +48,7 @@ SIGNATURES = {
     "bnp_imad32_peak": (_int, [_int, ctypes.POINTER(ctypes.c_double)]),
     "bnp_run_program_dev": (_int, [_int, ctypes.c_void_p, ctypes.c_char_p, _u64p, _u64p, _u64p, _u64p, _u64p, _sz]),
     "bnp_set_launch_config": (_int, [_int, _int]),
+    "bnp_threads_per_block": (_int, []),
 }
 
 
