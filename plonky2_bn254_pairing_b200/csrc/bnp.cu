@@ -173,7 +173,11 @@ int launch_T(DevCtx& c, const BnpProgram& p, int pidx, cudaStream_t st, u64* con
         occ_cache[key] = std::make_pair(per_sm, smem);
     }
     if (per_sm < 1) {
-        g_last_error = "program does not fit in shared memory";
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, kern);
+        g_last_error = "no block of " + std::to_string(T) + " threads fits an SM: " + std::to_string(smem) + " B dynamic + " +
+                       std::to_string(fa.sharedSizeBytes) + " B static shared memory, " + std::to_string(fa.numRegs) +
+                       " registers per thread";
         return BNP_EUNSUPPORTED;
     }
     const size_t n_chunks = (n + BNP_CHUNK - 1) / BNP_CHUNK;  // a warp works on 32 pairings, one per lane

@@ -382,6 +382,16 @@ __device__ __forceinline__ void fp_canon(u32* r, u32 lvl) {
                       (u32)BNP_P7);
 }
 
+// the upper steps of the ladder only: r in [0, 2p * (lvl + 1)) -> [0, 2p)
+__device__ __forceinline__ void fp_canon_upper(u32* r, u32 lvl) {
+    if (lvl >= 2u)
+        fp_cond_sub_const(r, 0x61f3f51cu, 0xf082305bu, 0xa1c72a34u, 0x5e05aa45u, 0x06056176u, 0xe14116dau, 0x84c680a6u,
+                          0xc19139cbu);  // 4p
+    if (lvl >= 1u)
+        fp_cond_sub_const(r, 0xb0f9fa8eu, 0x7841182du, 0xd0e3951au, 0x2f02d522u, 0x0302b0bbu, 0x70a08b6du, 0xc2634053u,
+                          0x60c89ce5u);  // 2p
+}
+
 // Montgomery reduction of a 512-bit T < p * 2^256: r = T / 2^256 mod p, canonical.
 // 8 IMAD + 64 IMAD.WIDE.
 // fp_redc_lazy: any T < 2^512 - p * 2^256; the result is T / 2^256 + (< p), NOT canonicalised.

@@ -57,6 +57,9 @@ __device__ __constant__ u32 BNP_CONSTS[BNP_MAX_CONST][16];
 // per access, 8 % of the kernel; profiles/experiments_r2.txt).  One 384-thread block per SM then holds 18 slots per
 // pairing instead of 9, and a fused pairing shrinks from 18 400 to 9 300 sequencer instructions (spills and re-loads
 // from 9 600 to 1 000); a 512-thread block holds 14 slots at 16 warps per SM.
+#ifndef BNP_LIN_PREFETCH
+#define BNP_LIN_PREFETCH 1
+#endif
 #ifndef BNP_ST_WAIT_LATE
 #define BNP_ST_WAIT_LATE 0
 #endif
@@ -219,12 +222,29 @@ __device__ __forceinline__ void vm_lin(const Slots<T>& S, Fp2& out, u32 n, const
     u64 E0[5], O0[5], E1[5], O1[5];
 #pragma unroll
     for (int i = 0; i < 5; i++) E0[i] = O0[i] = E1[i] = O1[i] = 0ull;
+#if BNP_LIN_PREFETCH
+    // the entry word of pair j + 1 is fetched while pair j is accumulated (the list is followed by at least one more
+    // program word, so reading one word past it is safe)
+    u32 tn = __ldg(ents);
+#pragma unroll 1
+    for (u32 j = 0; j < n; j++) {
+        u32 za[8], zb[8];
+        const u32 ta = tn;
+        tn = __ldg(ents + j + 1u);
+        S.issue_half(za, ta & 0xffu, (ta >> 8) & 1u);
+        S.issue_half(zb, (ta >> 16) & 0xffu, (ta >> 24) & 1u);
+        S.wait_half(za);
+        S.dep_half(zb);
+        BNP_LIN_ACC(za, zb, ta);
+    }
+#else
 #pragma unroll 1
     for (u32 j = 0; j < n; j++) {
         u32 za[8], zb[8], ta;
         BNP_LIN_FETCH(j, za, zb, ta);
         BNP_LIN_ACC(za, zb, ta);
     }
+#endif
     u32 v0[9], v1[9];
     lin_merge(v0, E0, O0);
     lin_merge(v1, E1, O1);
@@ -343,8 +363,15 @@ __device__ __forceinline__ void vm_product(const Slots<T>& S, u32 op, const u64*
     Fp2 r;
     fp_redc_lazy(r.c0, T0);
     fp_redc_lazy(r.c1, T1);
-    fp_canon(r.c0, (imm >> BNP_MUL_CANON_SHIFT) & 3u);
-    fp_canon(r.c1, (imm >> (BNP_MUL_CANON_SHIFT + 2)) & 3u);
+    // canonicalisation: the common case (both components below 2p) is ONE uniform test away from the final conditional
+    // subtraction - four separately guarded ladder steps were four reconvergence regions per product
+    const u32 cl = (imm >> BNP_MUL_CANON_SHIFT) & 15u;
+    if (cl) {
+        fp_canon_upper(r.c0, cl & 3u);
+        fp_canon_upper(r.c1, cl >> 2);
+    }
+    fp_cond_sub_p(r.c0);
+    fp_cond_sub_p(r.c1);
     if (!(imm & BNP_MUL_EXT)) {
         S.store(d, r);
         ins = w0;
@@ -452,14 +479,15 @@ __global__ void __launch_bounds__(T, (BNP_MINB * 64) / T > 0 ? (BNP_MINB * 64) /
             Fp2 x, y, r;
             // one dense switch: a jump table instead of a ladder of compares (the sequencer runs ~20 000
             // instructions per pairing; the ladder was 10 % of all stall samples)
+            // product-class opcodes (1, 2, 3) are two thirds of all instructions: one test, ahead of the switch
+            static_assert(BNP_OP_MUL == 1 && BNP_OP_SQR == 2 && BNP_OP_MULFP == 3, "product-class opcodes must be 1, 2, 3");
+            if (op - 1u < 3u) {
+                vm_product<T>(S, op, pc, ins, w0, d, a, b, c, ee, imm);
+                continue;
+            }
             switch (op) {
                 case BNP_OP_END:
                     running = false;
-                    break;
-                case BNP_OP_MUL:
-                case BNP_OP_SQR:
-                case BNP_OP_MULFP:
-                    vm_product<T>(S, op, pc, ins, w0, d, a, b, c, ee, imm);
                     break;
                 case BNP_OP_LIN: {  // d = LIN(slots), a = number of entry pairs
                     const u32 nw = (a + 1u) >> 1;
