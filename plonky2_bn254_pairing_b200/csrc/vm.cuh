@@ -58,7 +58,7 @@ __device__ __constant__ u32 BNP_CONSTS[BNP_MAX_CONST][16];
 // pairing instead of 9, and a fused pairing shrinks from 18 400 to 9 300 sequencer instructions (spills and re-loads
 // from 9 600 to 1 000); a 512-thread block holds 14 slots at 16 warps per SM.
 #ifndef BNP_LIN_PREFETCH
-#define BNP_LIN_PREFETCH 1
+#define BNP_LIN_PREFETCH 0
 #endif
 #ifndef BNP_ST_WAIT_LATE
 #define BNP_ST_WAIT_LATE 0
