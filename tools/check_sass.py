@@ -2,12 +2,13 @@
 
     python tools/check_sass.py [libbnp.so]
 
-  * registers <= 170: 12 warps of 64-thread blocks must fit an SM's register file;
+  * registers <= 170: the 12 warps of the 384-thread block must fit an SM's register file (3 warps x 32 x 170 per sub-partition);
   * every 32x32->64 multiply-accumulate is ONE instruction: IMAD.WIDE.U32[.X], or IMAD.HI.U32 for the first column of
     a Montgomery-reduction row (its low word is zero by construction, so ptxas keeps only the high half and the
     carry: 8 per reduction instance) - no mul.lo / mul.hi pairs left un-fused;
-  * the kernel stays below 4 096 instructions (64 KB): the code that runs more than 100 times per task must fit the
-    32 KB instruction cache.
+  * the kernel stays below 4 608 instructions (72 KB): the code that runs more than 100 times per task must fit the
+    32 KB instruction cache;
+  * the slot file really uses tensor memory: LDTM / STTM (tcgen05.ld / tcgen05.st) are present.
 Prints the mnemonic histogram; exits non-zero if a property fails."""
 import collections
 import os
@@ -58,6 +59,11 @@ def main(lib=None):
         ok = False
     if hi > MAX_IMAD_HI:
         print("FAIL:", hi, "IMAD.HI.U32 - un-fused multiply pairs?")
+        ok = False
+    tm = sum(v for k, v in hist.items() if k.startswith("LDTM") or k.startswith("STTM"))
+    print("tensor-memory accesses (LDTM / STTM):", tm)
+    if tm == 0:
+        print("FAIL: no LDTM / STTM - the tensor-memory half of the slot file is missing")
         ok = False
     if hist.get("IMAD.HI", 0):
         print("FAIL: signed IMAD.HI present")
