@@ -38,6 +38,7 @@ extern "C" {
 #define BNP_ECUDA (-3)    /* CUDA runtime error (see bnp_last_error) */
 #define BNP_ENOMEM (-4)
 #define BNP_EUNSUPPORTED (-5)
+#define BNP_EMALFORMED (-6) /* bnp_eip197_pairing_check: a point of the input is not a valid encoding */
 
 #define BNP_VARIANT_REFERENCE 0 /* exponent (p^12-1)/r, bit-equal to final_exp_native.rs:209 */
 #define BNP_VARIANT_ARK 1       /* ark-ec 0.4.2 Bn254 final exponentiation (= variant 0 ^ 2x(6x^2+3x+1)) */
@@ -117,6 +118,38 @@ uint64_t bnp_program_macs(const char* program);
 /* Multiply-accumulates the kernel actually issues for one element.  One thread runs a whole Karatsuba Fq2 operation,
  * so this equals bnp_program_macs (round 1's component-split kernel issued 15 % more). */
 uint64_t bnp_program_macs_executed(const char* program);
+
+/* ---- Wire formats decoded / encoded on the device -------------------------------------------------
+ * The reference takes ark-bn254 values; what a caller holds are bytes.  `fmt`:
+ *   BNP_WIRE_ARK_UNCOMPRESSED / BNP_WIRE_ARK_COMPRESSED  ark-serialize 0.4 CanonicalSerialize of G1Affine / G2Affine
+ *       (little-endian canonical integers, Fq2 as c0 || c1, flags in the two top bits of the last byte: bit 7 "y is the
+ *       larger of {y, -y}", bit 6 point at infinity); the compressed form recovers y by a square root on the device;
+ *   BNP_WIRE_EIP197  EIP-196/197 words: 32-byte big-endian, G1 = x || y, G2 = x.c1 || x.c0 || y.c1 || y.c0, zero = infinity.
+ * Element sizes: G1 64 / 32 / 64 bytes, G2 128 / 64 / 128 bytes.  Outputs are the SoA arrays the pairing entry points
+ * take; status[i] is one of BNP_POINT_*, and the coordinates of an element whose status is not BNP_POINT_OK are zero.
+ * `check_subgroup` adds the r-torsion test the reference hides in G2Affine::new (miller_loop_native.rs:303,311).
+ * Host pointers; the work runs on the first device of bnp_init. */
+#define BNP_WIRE_ARK_UNCOMPRESSED 0
+#define BNP_WIRE_ARK_COMPRESSED 1
+#define BNP_WIRE_EIP197 2
+#define BNP_POINT_OK 0
+#define BNP_POINT_INFINITY 1
+#define BNP_POINT_NOT_CANONICAL 2   /* a coordinate >= p, or both flag bits set */
+#define BNP_POINT_NOT_ON_CURVE 3    /* y^2 != x^3 + b, or (compressed) x^3 + b is not a square */
+#define BNP_POINT_NOT_IN_SUBGROUP 4 /* G2: on the twist, outside the r-torsion */
+int bnp_decode_g1_batch(int fmt, const uint8_t* in, size_t n, uint64_t* g1 /* [2][4][n] */, uint8_t* status /* [n] */);
+int bnp_decode_g2_batch(int fmt, const uint8_t* in, size_t n, uint64_t* g2 /* [4][4][n] */, uint8_t* status /* [n] */,
+                        int check_subgroup);
+/* MyFq12 SoA [12][4][n] <-> ark-serialize bytes of the ark Fq12 the reference's `Into<Fq12>` gives (pairing.rs:21):
+ * 384 bytes per element, c0.c0.c0, c0.c0.c1, c0.c1.c0, ... little-endian canonical integers. */
+int bnp_encode_fq12_batch(const uint64_t* f12, size_t n, uint8_t* out /* 384 n bytes */);
+int bnp_decode_fq12_batch(const uint8_t* in /* 384 n bytes */, size_t n, uint64_t* f12, uint8_t* status /* [n] */);
+/* The Ethereum pairing precompile (address 0x08, EIP-197) on `k` pairs of 192 bytes: *result = 1 iff
+ * e(P_1, Q_1) ... e(P_k, Q_k) == 1.  Decoding, curve and subgroup checks, Miller loops, product and final exponentiation
+ * all run on the device; pairs with a point at infinity drop out; returns BNP_EMALFORMED (precompile failure) when a
+ * point is not a canonical encoding, not on its curve, or (G2) not in the subgroup. */
+int bnp_eip197_pairing_check(const uint8_t* in, size_t k, int* result);
+
 /* Kernel launches issued by this library since bnp_init (for bench.py's gpu_launches). */
 uint64_t bnp_launch_count(void);
 /* Dependency-free IMAD.WIDE.U32 throughput microbenchmark on `device`: writes multiply-accumulates

@@ -164,6 +164,82 @@ def validate_soa(g1=None, g2=None):
     return ok
 
 
+# ----------------------------------------------------------------------------- wire formats
+WIRE_ARK_UNCOMPRESSED, WIRE_ARK_COMPRESSED, WIRE_EIP197 = 0, 1, 2
+POINT_OK, POINT_INFINITY, POINT_NOT_CANONICAL, POINT_NOT_ON_CURVE, POINT_NOT_IN_SUBGROUP = 0, 1, 2, 3, 4
+
+
+def _point_bytes(group, fmt):
+    full = 64 if group == 1 else 128
+    return full // 2 if fmt == WIRE_ARK_COMPRESSED else full
+
+
+def decode_g1_soa(fmt, data):
+    """bytes (n elements of 64 / 32 / 64 bytes for ark uncompressed / ark compressed / EIP-196) -> (uint64 [2][4][n]
+    Montgomery SoA, uint8 status [n]); decoding, range and curve checks and the compressed form's square root run on
+    the device (csrc/wire.cuh)."""
+    lib = native.lib()
+    size = _point_bytes(1, fmt)
+    assert len(data) % size == 0
+    n = len(data) // size
+    buf = np.frombuffer(bytes(data), dtype=np.uint8)
+    out = np.zeros((2, 4, n), dtype=np.uint64)
+    st = np.zeros(n, dtype=np.uint8)
+    native.check(lib.bnp_decode_g1_batch(fmt, buf.ctypes.data_as(ctypes.c_void_p), n, _ptr(out),
+                                         st.ctypes.data_as(ctypes.c_void_p)))
+    return out, st
+
+
+def decode_g2_soa(fmt, data, check_subgroup=True):
+    """bytes (128 / 64 / 128 per element) -> (uint64 [4][4][n], uint8 status [n]); `check_subgroup` adds the r-torsion
+    test of `G2Affine::new` (miller_loop_native.rs:303,311)."""
+    lib = native.lib()
+    size = _point_bytes(2, fmt)
+    assert len(data) % size == 0
+    n = len(data) // size
+    buf = np.frombuffer(bytes(data), dtype=np.uint8)
+    out = np.zeros((4, 4, n), dtype=np.uint64)
+    st = np.zeros(n, dtype=np.uint8)
+    native.check(lib.bnp_decode_g2_batch(fmt, buf.ctypes.data_as(ctypes.c_void_p), n, _ptr(out),
+                                         st.ctypes.data_as(ctypes.c_void_p), 1 if check_subgroup else 0))
+    return out, st
+
+
+def encode_fq12_soa(f):
+    """uint64 [12][4][n] MyFq12 SoA -> n * 384 bytes: ark-serialize of the ark Fq12 that `MyFq12::into()` gives."""
+    lib = native.lib()
+    n = f.shape[2]
+    out = np.zeros(384 * n, dtype=np.uint8)
+    native.check(lib.bnp_encode_fq12_batch(_ptr(f), n, out.ctypes.data_as(ctypes.c_void_p)))
+    return out.tobytes()
+
+
+def decode_fq12_soa(data):
+    lib = native.lib()
+    assert len(data) % 384 == 0
+    n = len(data) // 384
+    buf = np.frombuffer(bytes(data), dtype=np.uint8)
+    out = np.zeros((12, 4, n), dtype=np.uint64)
+    st = np.zeros(n, dtype=np.uint8)
+    native.check(lib.bnp_decode_fq12_batch(buf.ctypes.data_as(ctypes.c_void_p), n, _ptr(out),
+                                           st.ctypes.data_as(ctypes.c_void_p)))
+    return out, st
+
+
+def eip197_pairing_check(data):
+    """The Ethereum pairing precompile (EIP-197) on len(data) / 192 pairs: True iff the product of pairings is one.
+    Raises BnpError (BNP_EMALFORMED) where the precompile fails: a non-canonical coordinate, a point off its curve, a G2
+    point outside the subgroup."""
+    lib = native.lib()
+    if len(data) % 192:
+        raise native.BnpError("EIP-197 input length must be a multiple of 192 bytes")
+    k = len(data) // 192
+    buf = np.frombuffer(bytes(data), dtype=np.uint8) if k else np.zeros(1, dtype=np.uint8)
+    res = ctypes.c_int(0)
+    native.check(lib.bnp_eip197_pairing_check(buf.ctypes.data_as(ctypes.c_void_p), k, ctypes.byref(res)))
+    return bool(res.value)
+
+
 # ----------------------------------------------------------------------------- batched slice variants (north star)
 def miller_loop_native_batch(Qs, Ps):
     """[miller_loop_native(Q_i, P_i)]"""

@@ -18,6 +18,7 @@
 #include "../../include/bnp.h"
 #include "microcode_tables.h"
 #include "vm.cuh"
+#include "wire.cuh"
 
 // ok[e] = (first ? 1 : ok[e]) & (every limb of element e in the `rows` limb rows of `res` is zero)
 __global__ void bnp_zero_flags_kernel(const u64* res, u32 rows, size_t stride, size_t n, unsigned char* ok, int first) {
@@ -52,6 +53,8 @@ struct DevCtx {
     unsigned next_counter = 0;
     u64* pow_buf[2] = {nullptr, nullptr};  // work buffers of the run-time exponent walk (bnp_pow_u64_*)
     size_t pow_bytes[2] = {0, 0};
+    unsigned char* wire_buf[3] = {nullptr, nullptr, nullptr};  // wire formats: input bytes, status bytes, subgroup flags
+    size_t wire_bytes[3] = {0, 0, 0};
     // staging for the host-pointer API
     u64* stage[BNP_NARR] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t stage_bytes[BNP_NARR] = {0, 0, 0, 0, 0, 0};
@@ -567,6 +570,57 @@ int validate_dev_locked(DevCtx& c, void* stream, const u64* g1, const u64* g2, u
     return BNP_OK;
 }
 
+// ---- wire formats (wire.cuh): everything runs on the first device of bnp_init ----
+size_t wire_point_bytes(int group, int fmt) {
+    const size_t full = group == 1 ? 64 : 128;
+    return fmt == BNP_WIRE_ARK_COMPRESSED ? full / 2 : full;
+}
+
+// bytes already on the device at `d_in` (element e at d_in + e * stride) -> SoA in c.stage[group - 1], status bytes in
+// c.wire_buf[1 (G1) / 2 (G2)]; G2 optionally with the r-torsion test (sequencer program validate_g2)
+int wire_decode_dev_locked(DevCtx& c, int group, int fmt, const unsigned char* d_in, size_t stride, size_t n,
+                           int check_subgroup) {
+    int rc;
+    const size_t K = group == 1 ? 2 : 4;
+    if ((rc = ensure_stage(c, group - 1, K * 32 * n))) return rc;
+    const int sb = group;  // status buffer index
+    if ((rc = grow(c, c.stream, c.wire_buf[sb], c.wire_bytes[sb], n))) return rc;
+    const unsigned blocks = (unsigned)((n + 127) / 128);
+    if (group == 1)
+        bnp_decode_g1_kernel<<<blocks, 128, 0, c.stream>>>(fmt, d_in, stride, n, c.stage[0], c.wire_buf[sb]);
+    else
+        bnp_decode_g2_kernel<<<blocks, 128, 0, c.stream>>>(fmt, d_in, stride, n, c.stage[1], c.wire_buf[sb]);
+    CK(cudaGetLastError());
+    g_launches++;
+    if (group == 2 && check_subgroup) {
+        if ((rc = ensure_stage(c, 5, n))) return rc;
+        unsigned char* ok = reinterpret_cast<unsigned char*>(c.stage[5]);
+        if ((rc = validate_dev_locked(c, nullptr, nullptr, c.stage[1], ok, n))) return rc;
+        bnp_merge_subgroup_kernel<<<blocks, 128, 0, c.stream>>>(c.wire_buf[sb], ok, n, c.stage[1]);
+        CK(cudaGetLastError());
+    }
+    return BNP_OK;
+}
+
+int wire_decode_host(int group, int fmt, const uint8_t* in, size_t n, uint64_t* out, uint8_t* status, int check_subgroup) {
+    if (fmt < 0 || fmt > 2) return BNP_EINVAL;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ctx.empty()) return BNP_ENODEV;
+    if (n == 0) return BNP_OK;
+    if (!in || !out || !status) return BNP_EINVAL;
+    DevCtx& c = g_ctx[0];
+    CK(cudaSetDevice(c.dev));
+    const size_t bytes = wire_point_bytes(group, fmt), K = group == 1 ? 2 : 4;
+    int rc;
+    if ((rc = grow(c, c.stream, c.wire_buf[0], c.wire_bytes[0], bytes * n))) return rc;
+    CK(cudaMemcpyAsync(c.wire_buf[0], in, bytes * n, cudaMemcpyHostToDevice, c.stream));
+    if ((rc = wire_decode_dev_locked(c, group, fmt, c.wire_buf[0], bytes, n, check_subgroup))) return rc;
+    CK(cudaMemcpyAsync(out, c.stage[group - 1], K * 32 * n, cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaMemcpyAsync(status, c.wire_buf[group], n, cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    return BNP_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -633,6 +687,7 @@ const char* bnp_strerror(int code) {
         case BNP_ECUDA: return "CUDA error";
         case BNP_ENOMEM: return "out of memory";
         case BNP_EUNSUPPORTED: return "unsupported";
+        case BNP_EMALFORMED: return "malformed point encoding";
         default: return "unknown error";
     }
 }
@@ -773,6 +828,113 @@ int bnp_pairing_product(const uint64_t* g1, const uint64_t* g2, uint64_t* out, s
         return rc;
     CK(cudaMemcpyAsync(out, c0.stage[3], 384, cudaMemcpyDeviceToHost, c0.stream));
     return sync_all();
+}
+
+// ---- wire formats ----
+int bnp_decode_g1_batch(int fmt, const uint8_t* in, size_t n, uint64_t* g1, uint8_t* status) {
+    return wire_decode_host(1, fmt, in, n, g1, status, 0);
+}
+
+int bnp_decode_g2_batch(int fmt, const uint8_t* in, size_t n, uint64_t* g2, uint8_t* status, int check_subgroup) {
+    return wire_decode_host(2, fmt, in, n, g2, status, check_subgroup);
+}
+
+int bnp_encode_fq12_batch(const uint64_t* f12, size_t n, uint8_t* out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ctx.empty()) return BNP_ENODEV;
+    if (n == 0) return BNP_OK;
+    if (!f12 || !out) return BNP_EINVAL;
+    DevCtx& c = g_ctx[0];
+    CK(cudaSetDevice(c.dev));
+    int rc;
+    if ((rc = ensure_stage(c, 2, 384 * n))) return rc;
+    if ((rc = grow(c, c.stream, c.wire_buf[0], c.wire_bytes[0], 384 * n))) return rc;
+    CK(cudaMemcpyAsync(c.stage[2], f12, 384 * n, cudaMemcpyHostToDevice, c.stream));
+    bnp_encode_fq12_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c.stream>>>(c.stage[2], n, c.wire_buf[0]);
+    CK(cudaGetLastError());
+    g_launches++;
+    CK(cudaMemcpyAsync(out, c.wire_buf[0], 384 * n, cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    return BNP_OK;
+}
+
+int bnp_decode_fq12_batch(const uint8_t* in, size_t n, uint64_t* f12, uint8_t* status) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ctx.empty()) return BNP_ENODEV;
+    if (n == 0) return BNP_OK;
+    if (!in || !f12 || !status) return BNP_EINVAL;
+    DevCtx& c = g_ctx[0];
+    CK(cudaSetDevice(c.dev));
+    int rc;
+    if ((rc = ensure_stage(c, 2, 384 * n))) return rc;
+    if ((rc = grow(c, c.stream, c.wire_buf[0], c.wire_bytes[0], 384 * n))) return rc;
+    if ((rc = grow(c, c.stream, c.wire_buf[1], c.wire_bytes[1], n))) return rc;
+    CK(cudaMemcpyAsync(c.wire_buf[0], in, 384 * n, cudaMemcpyHostToDevice, c.stream));
+    bnp_decode_fq12_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c.stream>>>(c.wire_buf[0], n, c.stage[2], c.wire_buf[1]);
+    CK(cudaGetLastError());
+    g_launches++;
+    CK(cudaMemcpyAsync(f12, c.stage[2], 384 * n, cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaMemcpyAsync(status, c.wire_buf[1], n, cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    return BNP_OK;
+}
+
+int bnp_eip197_pairing_check(const uint8_t* in, size_t k, int* result) {
+    if (!result || (k && !in)) return BNP_EINVAL;
+    std::vector<u64> g1, g2;
+    size_t m = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (g_ctx.empty()) return BNP_ENODEV;
+        if (k == 0) {
+            *result = 1;  // the empty product
+            return BNP_OK;
+        }
+        DevCtx& c = g_ctx[0];
+        CK(cudaSetDevice(c.dev));
+        int rc;
+        if ((rc = grow(c, c.stream, c.wire_buf[0], c.wire_bytes[0], 192 * k))) return rc;
+        CK(cudaMemcpyAsync(c.wire_buf[0], in, 192 * k, cudaMemcpyHostToDevice, c.stream));
+        if ((rc = wire_decode_dev_locked(c, 1, BNP_WIRE_EIP197, c.wire_buf[0], 192, k, 0))) return rc;
+        if ((rc = wire_decode_dev_locked(c, 2, BNP_WIRE_EIP197, c.wire_buf[0] + 64, 192, k, 1))) return rc;
+        std::vector<unsigned char> s1(k), s2(k);
+        std::vector<u64> h1(8 * k), h2(16 * k);
+        CK(cudaMemcpyAsync(s1.data(), c.wire_buf[1], k, cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaMemcpyAsync(s2.data(), c.wire_buf[2], k, cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaMemcpyAsync(h1.data(), c.stage[0], 64 * k, cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaMemcpyAsync(h2.data(), c.stage[1], 128 * k, cudaMemcpyDeviceToHost, c.stream));
+        CK(cudaStreamSynchronize(c.stream));
+        for (size_t i = 0; i < k; i++)
+            if (s1[i] >= BNP_PT_NOT_CANONICAL || s2[i] >= BNP_PT_NOT_CANONICAL) {
+                g_last_error = "EIP-197 input: pair " + std::to_string(i) + " is malformed (G1 status " +
+                               std::to_string(s1[i]) + ", G2 status " + std::to_string(s2[i]) + ")";
+                return BNP_EMALFORMED;
+            }
+        // e(P, O) = e(O, Q) = 1: pairs with a point at infinity drop out of the product
+        std::vector<size_t> keep;
+        for (size_t i = 0; i < k; i++)
+            if (s1[i] == BNP_PT_OK && s2[i] == BNP_PT_OK) keep.push_back(i);
+        m = keep.size();
+        g1.resize(8 * m);
+        g2.resize(16 * m);
+        for (size_t r = 0; r < 8; r++)
+            for (size_t j = 0; j < m; j++) g1[r * m + j] = h1[r * k + keep[j]];
+        for (size_t r = 0; r < 16; r++)
+            for (size_t j = 0; j < m; j++) g2[r * m + j] = h2[r * k + keep[j]];
+    }
+    if (m == 0) {
+        *result = 1;
+        return BNP_OK;
+    }
+    u64 out[48];
+    int rc = bnp_pairing_product(g1.data(), g2.data(), out, m, 0);
+    if (rc) return rc;
+    // one in MyFq12 / Montgomery form: coefficient 0 = R mod p, everything else zero
+    static const u64 one[4] = {0xd35d438dc58f0d9dull, 0x0a78eb28f5c70b3dull, 0x666ea36f7879462cull, 0x0e0a77c19a07df2full};
+    bool is_one = true;
+    for (int r = 0; r < 48; r++) is_one = is_one && out[r] == (r < 4 ? one[r] : 0ull);
+    *result = is_one ? 1 : 0;
+    return BNP_OK;
 }
 
 // ---- device-pointer variants ----

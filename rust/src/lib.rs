@@ -292,3 +292,48 @@ pub fn conjugate_fp2(x: Fq2) -> Fq2 {
 pub fn neg_conjugate_fp2(x: Fq2) -> Fq2 {
     Fq2::new(-x.c0, x.c1)
 }
+
+// ---- wire formats decoded on the device -------------------------------------
+/// `CanonicalSerialize::serialize_compressed` bytes of `n` G1Affine / G2Affine points (32 / 64 bytes each) straight
+/// into the batched pairing: decompression (the square roots), curve and subgroup checks run on the GPU.
+/// Panics - like `G1Affine::deserialize_compressed(..).unwrap()` would - if a point is malformed; points at infinity are
+/// not accepted (the reference's Miller loop has no meaning for them).
+pub fn pairing_batch_from_compressed(g1_bytes: &[u8], g2_bytes: &[u8]) -> Vec<Fq12> {
+    assert!(g1_bytes.len() % 32 == 0 && g2_bytes.len() == 2 * g1_bytes.len());
+    let n = g1_bytes.len() / 32;
+    init();
+    let (mut g1, mut g2) = (vec![0u64; 8 * n], vec![0u64; 16 * n]);
+    let (mut s1, mut s2) = (vec![0u8; n], vec![0u8; n]);
+    check(unsafe { ffi::bnp_decode_g1_batch(ffi::BNP_WIRE_ARK_COMPRESSED, g1_bytes.as_ptr(), n, g1.as_mut_ptr(), s1.as_mut_ptr()) });
+    check(unsafe { ffi::bnp_decode_g2_batch(ffi::BNP_WIRE_ARK_COMPRESSED, g2_bytes.as_ptr(), n, g2.as_mut_ptr(), s2.as_mut_ptr(), 1) });
+    for e in 0..n {
+        assert!(s1[e] == ffi::BNP_POINT_OK && s2[e] == ffi::BNP_POINT_OK, "pair {e}: G1 status {}, G2 status {}", s1[e], s2[e]);
+    }
+    let mut out = vec![0u64; 48 * n];
+    check(unsafe { ffi::bnp_pairing_batch(g1.as_ptr(), g2.as_ptr(), out.as_mut_ptr(), n, ffi::BNP_VARIANT_REFERENCE) });
+    unpack_fq12(&out, n).into_iter().map(|f| f.into()).collect()
+}
+
+/// `serialize_compressed` bytes (384 per element) of the ark `Fq12` values a batch of `MyFq12` converts into.
+pub fn fq12_to_bytes_batch(fs: &[MyFq12]) -> Vec<u8> {
+    init();
+    let mut out = vec![0u8; 384 * fs.len()];
+    check(unsafe { ffi::bnp_encode_fq12_batch(pack_fq12(fs).as_ptr(), fs.len(), out.as_mut_ptr()) });
+    out
+}
+
+/// The Ethereum pairing precompile (address 0x08, EIP-197): `Some(true / false)`, or `None` where the precompile fails
+/// (a coordinate >= p, a point off its curve, a G2 point outside the subgroup, a length that is not a multiple of 192).
+pub fn eip197_pairing_check(input: &[u8]) -> Option<bool> {
+    if input.len() % 192 != 0 {
+        return None;
+    }
+    init();
+    let mut res: core::ffi::c_int = 0;
+    let rc = unsafe { ffi::bnp_eip197_pairing_check(input.as_ptr(), input.len() / 192, &mut res) };
+    if rc == ffi::BNP_EMALFORMED {
+        return None;
+    }
+    check(rc);
+    Some(res == 1)
+}

@@ -69,3 +69,33 @@ fn ark_variant_equals_bn254_pairing() {
     let got = gpu::pairing_batch_variant(&[p], &[q], 1).remove(0);
     assert_eq!(got, want);
 }
+
+
+/// the byte formats csrc/wire.cuh decodes are ark-serialize's - pinned here against the crate itself
+/// (oracle/wire_formats.py restates them without being able to run it).
+#[test]
+fn wire_formats_match_ark_serialize() {
+    use ark_serialize::CanonicalSerialize;
+    let mut rng = ark_std::test_rng();
+    let n = 32;
+    let ps: Vec<G1Affine> = (0..n).map(|_| G1Affine::rand(&mut rng)).collect();
+    let qs: Vec<G2Affine> = (0..n).map(|_| G2Affine::rand(&mut rng)).collect();
+    let (mut b1, mut b2) = (Vec::new(), Vec::new());
+    for (p, q) in ps.iter().zip(qs.iter()) {
+        p.serialize_compressed(&mut b1).unwrap();
+        q.serialize_compressed(&mut b2).unwrap();
+    }
+    let got = gpu::pairing_batch_from_compressed(&b1, &b2);
+    for i in 0..n {
+        assert_eq!(got[i], reference::pairing::pairing(ps[i], qs[i]));
+    }
+    // Fq12 bytes
+    let fs: Vec<_> = ps.iter().zip(qs.iter()).map(|(p, q)| reference::miller_loop_native::miller_loop_native(q, p)).collect();
+    let bytes = gpu::fq12_to_bytes_batch(&fs);
+    for (i, f) in fs.iter().enumerate() {
+        let mut want = Vec::new();
+        let a: Fq12 = f.clone().into();
+        a.serialize_compressed(&mut want).unwrap();
+        assert_eq!(&bytes[384 * i..384 * (i + 1)], &want[..]);
+    }
+}
