@@ -119,6 +119,21 @@ uint64_t bnp_program_macs(const char* program);
  * so this equals bnp_program_macs (round 1's component-split kernel issued 15 % more). */
 uint64_t bnp_program_macs_executed(const char* program);
 
+/* ---- Prepared G2 points ------------------------------------------------------------------------------
+ * The engine's `G2Prepared`: the 91 line-coefficient triples of one G2 point (BNP_PREP_FQ = 546 Fq per point, the same
+ * list ark-ec's `G2Prepared::from` builds, in this engine's normalisation).  A pairing whose G2 point is prepared skips
+ * all point arithmetic of the Miller loop; a Groth16 verifier prepares the three G2 points of its verifying key once.
+ *   bnp_g2_prepare_batch:       g2 [4][4][n] -> coeffs [BNP_PREP_FQ][4][n]
+ *   bnp_pairing_prepared_batch: out[i] = final_exp( prod_{j < kv} miller(g1[j], g2[j])  *  prod_{j < kp} miller(g1[kv + j], prepared[j]) )
+ *       g1 [2 (kv + kp)][4][n], g2 [4 kv][4][n] (NULL when kv = 0); `prepared` is ONE element, [kp * BNP_PREP_FQ][4][1],
+ *       shared by the whole batch.  Shapes in the library: (kv, kp) = (0, 1), (1, 2), (1, 3). */
+#define BNP_PREP_FQ 546
+int bnp_g2_prepare_batch(const uint64_t* g2, uint64_t* coeffs, size_t n);
+int bnp_pairing_prepared_batch(const uint64_t* g1, const uint64_t* g2, const uint64_t* prepared, uint64_t* out, size_t n,
+                               int kv, int kp, int variant);
+int bnp_pairing_prepared_dev(int device, void* stream, const uint64_t* g1, const uint64_t* g2, const uint64_t* prepared,
+                             uint64_t* out, size_t n, int kv, int kp, int variant);
+
 /* ---- Wire formats decoded / encoded on the device -------------------------------------------------
  * The reference takes ark-bn254 values; what a caller holds are bytes.  `fmt`:
  *   BNP_WIRE_ARK_UNCOMPRESSED / BNP_WIRE_ARK_COMPRESSED  ark-serialize 0.4 CanonicalSerialize of G1Affine / G2Affine

@@ -164,6 +164,31 @@ def validate_soa(g1=None, g2=None):
     return ok
 
 
+# ----------------------------------------------------------------------------- prepared G2 points
+PREP_FQ = 546
+
+
+def g2_prepare_soa(g2):
+    """uint64 [4][4][n] -> [PREP_FQ][4][n]: the line coefficients of every point (the engine's `G2Prepared`)."""
+    lib = native.lib()
+    n = g2.shape[2]
+    out = np.empty((PREP_FQ, 4, n), dtype=np.uint64)
+    native.check(lib.bnp_g2_prepare_batch(_ptr(g2), _ptr(out), n))
+    return out
+
+
+def pairing_prepared_soa(g1, g2, prepared, kv, kp, variant=VARIANT_REFERENCE):
+    """g1 [2 (kv + kp)][4][n], g2 [4 kv][4][n] or None, prepared [kp * PREP_FQ][4][1] (shared by the batch) ->
+    [12][4][n]: the product of kv + kp pairings per element, the last kp against the prepared points."""
+    lib = native.lib()
+    n = g1.shape[2]
+    assert g1.shape[0] == 2 * (kv + kp) and prepared.shape == (kp * PREP_FQ, 4, 1)
+    out = np.empty((12, 4, n), dtype=np.uint64)
+    native.check(lib.bnp_pairing_prepared_batch(_ptr(g1), _ptr(g2) if kv else None, _ptr(prepared), _ptr(out), n, kv, kp,
+                                                variant))
+    return out
+
+
 # ----------------------------------------------------------------------------- wire formats (SURVEY 8(f).3)
 WIRE_ARK_UNCOMPRESSED, WIRE_ARK_COMPRESSED, WIRE_EIP197 = 0, 1, 2
 POINT_OK, POINT_INFINITY, POINT_NOT_CANONICAL, POINT_NOT_ON_CURVE, POINT_NOT_IN_SUBGROUP = 0, 1, 2, 3, 4

@@ -111,7 +111,7 @@ int grow(DevCtx& c, cudaStream_t st, P*& buf, size_t& have, size_t need) {
 
 template <int T>
 int launch_T(DevCtx& c, const BnpProgram& p, int pidx, cudaStream_t st, u64* const arr[BNP_NARR], size_t n,
-             size_t stride) {
+             size_t stride, bool aux_bcast) {
     auto kern = bnp_vm_kernel<T>;
     // phase-split variants "name#K.i" (microcode/phases.py): the library holds a few phase counts K per program
     int var_idx[BNP_MAX_PHASES + 1][BNP_MAX_PHASES];
@@ -216,6 +216,7 @@ int launch_T(DevCtx& c, const BnpProgram& p, int pidx, cudaStream_t st, u64* con
     VmArgs a;
     for (int i = 0; i < BNP_MAX_PHASES; i++) a.prog[i] = c.d_prog[pidx];
     a.n_phases = 1;
+    a.aux_bcast = aux_bcast ? 1u : 0u;
     a.progress = nullptr;
     for (int i = 0; i < BNP_NARR; i++) a.arr[i] = arr[i];
     if (split) {
@@ -248,7 +249,7 @@ int launch_T(DevCtx& c, const BnpProgram& p, int pidx, cudaStream_t st, u64* con
 
 // run one program over n elements on device arrays
 int launch(DevCtx& c, const char* prog, void* stream, const u64* g1, const u64* g2, const u64* f12, const u64* aux,
-           u64* out, size_t n, size_t stride = 0) {
+           u64* out, size_t n, size_t stride = 0, bool aux_bcast = false) {
     if (n == 0) return BNP_OK;
     if (n > 0x7fffffffull) return BNP_EINVAL;
     int pidx = -1;
@@ -263,13 +264,13 @@ int launch(DevCtx& c, const char* prog, void* stream, const u64* g1, const u64* 
                           const_cast<u64*>(aux), nullptr};
     if (stride == 0) stride = n;
     switch (g_threads_per_block) {
-        case 32: return launch_T<32>(c, *p, pidx, st, arr, n, stride);
-        case 128: return launch_T<128>(c, *p, pidx, st, arr, n, stride);
-        case 256: return launch_T<256>(c, *p, pidx, st, arr, n, stride);
-        case 384: return launch_T<384>(c, *p, pidx, st, arr, n, stride);
-        case 448: return launch_T<448>(c, *p, pidx, st, arr, n, stride);
-        case 512: return launch_T<512>(c, *p, pidx, st, arr, n, stride);
-        default: return launch_T<64>(c, *p, pidx, st, arr, n, stride);
+        case 32: return launch_T<32>(c, *p, pidx, st, arr, n, stride, aux_bcast);
+        case 128: return launch_T<128>(c, *p, pidx, st, arr, n, stride, aux_bcast);
+        case 256: return launch_T<256>(c, *p, pidx, st, arr, n, stride, aux_bcast);
+        case 384: return launch_T<384>(c, *p, pidx, st, arr, n, stride, aux_bcast);
+        case 448: return launch_T<448>(c, *p, pidx, st, arr, n, stride, aux_bcast);
+        case 512: return launch_T<512>(c, *p, pidx, st, arr, n, stride, aux_bcast);
+        default: return launch_T<64>(c, *p, pidx, st, arr, n, stride, aux_bcast);
     }
 }
 
@@ -828,6 +829,55 @@ int bnp_pairing_product(const uint64_t* g1, const uint64_t* g2, uint64_t* out, s
         return rc;
     CK(cudaMemcpyAsync(out, c0.stage[3], 384, cudaMemcpyDeviceToHost, c0.stream));
     return sync_all();
+}
+
+// ---- prepared G2 points ----
+int bnp_g2_prepare_batch(const uint64_t* g2, uint64_t* coeffs, size_t n) {
+    return run_host("g2_prepare", {{1, g2, 4}}, coeffs, BNP_PREP_FQ, n);
+}
+
+int bnp_pairing_prepared_batch(const uint64_t* g1, const uint64_t* g2, const uint64_t* prepared, uint64_t* out, size_t n,
+                               int kv, int kp, int variant) {
+    if ((variant != 0 && variant != 1) || kv < 0 || kp < 1) return BNP_EINVAL;
+    const std::string prog = "pairing_p" + std::to_string(kv) + "_" + std::to_string(kp) + "_v" + std::to_string(variant);
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ctx.empty()) return BNP_ENODEV;
+    if (!find_program(prog.c_str())) {
+        g_last_error = "no program for " + std::to_string(kv) + " live + " + std::to_string(kp) + " prepared pairs";
+        return BNP_EUNSUPPORTED;
+    }
+    if (n == 0) return BNP_OK;
+    if (!g1 || !prepared || !out || (kv && !g2)) return BNP_EINVAL;
+    const size_t k = (size_t)kv + (size_t)kp;
+    auto parts = split_range(n, g_ctx.size());
+    for (size_t d = 0; d < g_ctx.size(); d++) {
+        if (parts[d].cnt == 0) continue;
+        DevCtx& c = g_ctx[d];
+        CK(cudaSetDevice(c.dev));
+        int rc;
+        if ((rc = copy_in(c, 0, g1, 2 * k, n, parts[d].off, parts[d].cnt))) return rc;
+        if (kv && (rc = copy_in(c, 1, g2, 4 * (size_t)kv, n, parts[d].off, parts[d].cnt))) return rc;
+        // the prepared points are ONE element ([kp * BNP_PREP_FQ][4][1]) that every pairing of the batch reads
+        if ((rc = ensure_stage(c, 4, (size_t)kp * BNP_PREP_FQ * 32))) return rc;
+        CK(cudaMemcpyAsync(c.stage[4], prepared, (size_t)kp * BNP_PREP_FQ * 32, cudaMemcpyHostToDevice, c.stream));
+        if ((rc = ensure_stage(c, 3, 384 * parts[d].cnt))) return rc;
+        if ((rc = launch(c, prog.c_str(), nullptr, c.stage[0], kv ? c.stage[1] : nullptr, nullptr, c.stage[4], c.stage[3],
+                         parts[d].cnt, 0, true)))
+            return rc;
+        if ((rc = copy_out(c, 3, out, 12, n, parts[d].off, parts[d].cnt))) return rc;
+    }
+    return sync_all();
+}
+
+int bnp_pairing_prepared_dev(int device, void* stream, const uint64_t* g1, const uint64_t* g2, const uint64_t* prepared,
+                             uint64_t* out, size_t n, int kv, int kp, int variant) {
+    if ((variant != 0 && variant != 1) || kv < 0 || kp < 1) return BNP_EINVAL;
+    const std::string prog = "pairing_p" + std::to_string(kv) + "_" + std::to_string(kp) + "_v" + std::to_string(variant);
+    std::lock_guard<std::mutex> lk(g_mu);
+    DevCtx* c = find_ctx(device);
+    if (!c) return BNP_ENODEV;
+    if (!find_program(prog.c_str())) return BNP_EUNSUPPORTED;
+    return launch(*c, prog.c_str(), stream, g1, g2, nullptr, prepared, out, n, 0, true);
 }
 
 // ---- wire formats ----

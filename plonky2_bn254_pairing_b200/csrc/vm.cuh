@@ -36,6 +36,7 @@ struct VmArgs {
     u32* counter;           // work counter (zeroed before launch): warps claim (phase, 32-element chunk) tasks
     u32* progress;          // per chunk: number of completed phases (zeroed before launch; unused when n_phases == 1)
     u32 n_phases;
+    u32 aux_bcast;          // the AUX array holds one element that every element of the batch reads (stride 1, index 0)
     u32 tmem_cols;          // TMEM columns this block allocates (a power of two >= 32)
     u32 tmem_cols_per_warp; // 8 * number of slots: the column range of one warp
 };
@@ -508,22 +509,29 @@ __global__ void __launch_bounds__(T, (BNP_MINB * 64) / T > 0 ? (BNP_MINB * 64) /
                     ins = w0;
                     pc++;
                     break;
-                case BNP_OP_LDG:
-                    ldg_fp(r.c0, args.arr[imm], a, stride, e);
-                    ldg_fp(r.c1, args.arr[imm], b, stride, e);
+                case BNP_OP_LDG: {
+                    // imm = array id | page << 8 (Fq index = page * 256 + field byte).  The AUX array may be ONE element
+                    // shared by the whole batch (prepared G2 points of a verifying key): every lane reads element 0.
+                    const u32 arr_id = imm & 0xffu, pg = (imm >> 8) << 8;
+                    const bool bc = arr_id == BNP_ARR_AUX && args.aux_bcast;
+                    ldg_fp(r.c0, args.arr[arr_id], pg + a, bc ? 1u : stride, bc ? 0u : e);
+                    ldg_fp(r.c1, args.arr[arr_id], pg + b, bc ? 1u : stride, bc ? 0u : e);
                     S.store(d, r);
                     ins = w0;
                     pc++;
                     break;
-                case BNP_OP_STG:
+                }
+                case BNP_OP_STG: {
                     S.load(x, a);
+                    const u32 pg = (imm >> 8) << 8;
                     if (active) {
-                        stg_fp(args.arr[imm], d, stride, e, x.c0);
-                        stg_fp(args.arr[imm], b, stride, e, x.c1);
+                        stg_fp(args.arr[imm & 0xffu], pg + d, stride, e, x.c0);
+                        stg_fp(args.arr[imm & 0xffu], pg + b, stride, e, x.c1);
                     }
                     ins = w0;
                     pc++;
                     break;
+                }
                 case BNP_OP_SPILL: {
                     S.load(x, a);
                     uint4* q = scr + (size_t)imm * 4 * total;

@@ -98,7 +98,8 @@ def allocate(ops, n_slots):
         if o.op == "LDC":
             emit("LDC", d=s, imm=o.imm)
         elif o.op == "LDG":
-            emit("LDG", d=s, a=o.f_lo, b=o.f_hi, imm=o.imm)
+            lo, hi, imm = isa.ldst_fields(o.f_lo, o.f_hi, o.imm)
+            emit("LDG", d=s, a=lo, b=hi, imm=imm)
         else:
             emit("FILL", d=s, imm=scratch_of[v])
         loc[v] = s
@@ -175,7 +176,8 @@ def allocate(ops, n_slots):
         elif o.op in ("ADD", "SUB"):
             emit(o.op, d=d, a=src_slots[0], b=src_slots[1])
         elif o.op == "STG":
-            emit("STG", d=o.f_lo, a=src_slots[0], b=o.f_hi, imm=o.imm)
+            lo, hi, imm = isa.ldst_fields(o.f_lo, o.f_hi, o.imm)
+            emit("STG", d=lo, a=src_slots[0], b=hi, imm=imm)
         elif o.op == "LIN":
 
             def enc(lst):

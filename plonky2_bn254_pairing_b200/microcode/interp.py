@@ -112,9 +112,11 @@ def run(words, consts, arrays, n_slots, n_scratch):
         elif op == "LDC":
             slots[d] = consts[imm]
         elif op == "LDG":
-            slots[d] = (arrays[imm][a], arrays[imm][b])
+            pg = (imm >> 8) << 8
+            slots[d] = (arrays[imm & 0xFF][pg + a], arrays[imm & 0xFF][pg + b])
         elif op == "STG":
-            arrays[imm][d], arrays[imm][b] = slots[a]
+            pg = (imm >> 8) << 8
+            arrays[imm & 0xFF][pg + d], arrays[imm & 0xFF][pg + b] = slots[a]
         elif op == "SPILL":
             scratch[imm] = slots[a]
         elif op == "FILL":

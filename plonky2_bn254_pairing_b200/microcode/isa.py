@@ -11,6 +11,8 @@ flow is uniform across the grid.  One instruction word is 64 bits, eight byte-wi
     byte 4  c     source slot
     byte 5  e     source slot
     byte 6-7 imm  16-bit immediate (constant index, array id, scratch index, flags)
+LDG / STG: imm = array id | page << 8; the Fq indices are page * 256 + the byte fields (both halves of a value lie in one
+page), so that an array can hold more than 256 Fq per element (the line coefficients of prepared G2 points).
 
 MUL / SQR take optional pre-additions (Karatsuba operands are sums of two slots):
     MUL  d = (a [+-b]) * (c [+-e])     imm bit0: b present, bit1: b subtracted, bit2: e present, bit3: e subtracted
@@ -214,6 +216,13 @@ def emit_c_defines():
     s = "".join("#define BNP_OP_%s %d\n" % (name, i) for i, name in enumerate(OPS))
     s += "#define BNP_MUL_B %d\n#define BNP_MUL_BNEG %d\n#define BNP_MUL_E %d\n#define BNP_MUL_ENEG %d\n" % (
         MUL_B, MUL_BNEG, MUL_E, MUL_ENEG)
+    s += "#define BNP_ARR_AUX %d\n" % ARR_AUX
     s += "#define BNP_MUL_EXT %d\n#define BNP_MUL_CANON_SHIFT %d\n#define BNP_EXT_STORE_R %d\n#define BNP_MULFP_HALF %d\n#define BNP_MUL_BCANON %d\n" % (
         MUL_EXT, MUL_CANON_SHIFT, EXT_STORE_R, MULFP_HALF, MUL_BCANON)
     return s
+
+
+def ldst_fields(f_lo, f_hi, arr):
+    """(low byte of f_lo, low byte of f_hi, imm) of an LDG / STG on Fq indices f_lo, f_hi of array `arr`."""
+    assert 0 <= arr <= 0xFF and f_lo >> 8 == f_hi >> 8 and f_lo >> 8 <= 0xFF, (f_lo, f_hi)
+    return f_lo & 0xFF, f_hi & 0xFF, arr | ((f_lo >> 8) << 8)

@@ -38,18 +38,22 @@ _C3 = c_mul(_C2, _C1)
 
 
 class _Pair:
-    """Per-pair state of the projective Miller loop."""
+    """Per-pair state of the projective Miller loop.  Every step yields a P-INDEPENDENT coefficient triple (c0, c1, c2)
+    - what ark calls an `EllCoeff` of `G2Prepared`, in this engine's normalisation - and its evaluation at P,
+    (e0, e1, e3) = (c0 * s0, c1 * s1, c2) with Fq scalars s0, s1 taken from P.  `with_p=False` builds the coefficients
+    only (program g2_prepare)."""
 
-    def __init__(self, b, pair_index):
+    def __init__(self, b, pair_index, with_p=True, g2_index=None):
         k = pair_index
         self.b = b
-        self.Pv = b.ldg(isa.ARR_G1, 2 * k, 2 * k + 1)  # (xP, yP) packed in one slot
-        self.Qx = b.ldg(isa.ARR_G2, 4 * k, 4 * k + 1)
-        self.Qy = b.ldg(isa.ARR_G2, 4 * k + 2, 4 * k + 3)
-        # (-3 xP, -yP): scalars for the tangent's w^4 coefficient and the chord's w^2 coefficient
-        m3 = -b.times(self.Pv, 3)
-        self.Pn = m3  # c0 = -3 xP (c1 = -3 yP unused)
-        self.Pm = -self.Pv  # c1 = -yP
+        if with_p:
+            self.Pv = b.ldg(isa.ARR_G1, 2 * k, 2 * k + 1)  # (xP, yP) packed in one slot
+            # (-3 xP, -yP): scalars for the tangent's w^4 coefficient and the chord's w^2 coefficient
+            self.Pn = -b.times(self.Pv, 3)  # c0 = -3 xP (c1 = -3 yP unused)
+            self.Pm = -self.Pv  # c1 = -yP
+        j = k if g2_index is None else g2_index
+        self.Qx = b.ldg(isa.ARR_G2, 4 * j, 4 * j + 1)
+        self.Qy = b.ldg(isa.ARR_G2, 4 * j + 2, 4 * j + 3)
         self.nQy = None
         self.X, self.Y, self.Z = self.Qx, self.Qy, b.const((1, 0))
 
@@ -58,11 +62,12 @@ class _Pair:
             self.nQy = -self.Qy
         return self.nQy
 
-    def double_step(self):
-        """Tangent at R and R <- 2R.  Returns the line as (e0, e1, e3) of  xi*Z^2/w^3 * tangent_ref:
+    # ---- P-independent halves
+    def tangent_coeffs(self):
+        """Tangent at R and R <- 2R.  Returns (c0, c1, c2) = (xi 2YZ, xi X^2, xi Y^2 - 9 Z^2):
               tangent_ref*Z^2 = l0 + l3 w^3 + l4 w^4,  l0 = xi Y^2 - 9 Z^2, l3 = 2YZ yP, l4 = -3 X^2 xP
               (miller_loop_native.rs:30-44 with the curve equation substituted)
-           and (e0, e1, e3) = (xi l3, xi l4, l0).
+           and the line multiplied into f is xi*Z^2/w^3 * tangent_ref = (xi l3) + (xi l4) w + l0 w^3.
         Doubling: Costello-Lange-Naehrig homogeneous formulas for y^2 = x^3 + 3/xi, with the whole
         triple scaled by 4 xi^2 so that neither a halving nor the constant 3/xi is needed."""
         b = self.b
@@ -76,25 +81,23 @@ class _Pair:
         F27 = b.times(E9, 3)
         xiH = H.mulxi()
         l0 = Bx - E9
-        e0 = xiH.mulfp(self.Pv, 1)  # xi * 2YZ * yP
-        e1 = J.mulxi().mulfp(self.Pn, 0)  # xi * X^2 * (-3 xP)
+        xiJ = J.mulxi()
         XY2 = (X * Y).dbl()
         self.X = (XY2 * (Bx - F27)).mulxi()
         G2 = Bx + F27
         self.Y = G2.sqr() - b.times(E9.sqr(), 12)
         self.Z = b.times(Bx * xiH, 4)
-        return e0, e1, l0
+        return xiH, xiJ, l0
 
-    def add_step(self, x2, y2, update=True):
-        """Chord through R and the affine point (x2, y2), then R <- R + (x2, y2).
-        Returns (e0, e1, e3) = (l2, l3, l5) of  Z/w^2 * chord_ref:
+    def chord_coeffs(self, x2, y2, update=True):
+        """Chord through R and the affine point (x2, y2), then R <- R + (x2, y2).  Returns (c0, c1, c2) =
+        (X - x2 Z, Y - y2 Z, X y2 - x2 Y):
               chord_ref*Z = l2 w^2 + l3 w^3 + l5 w^5,
-              l2 = (x2 Z - X) yP,  l3 = (Y - y2 Z) xP,  l5 = X y2 - x2 Y     (miller_loop_native.rs:10-28)"""
+              l2 = (x2 Z - X) yP,  l3 = (Y - y2 Z) xP,  l5 = X y2 - x2 Y     (miller_loop_native.rs:10-28)
+        and the line multiplied into f is Z/w^2 * chord_ref = l2 + l3 w + l5 w^3."""
         X, Y, Z = self.X, self.Y, self.Z
         theta = Y - y2 * Z
         lam = X - x2 * Z
-        l2 = lam.mulfp(self.Pm, 1)  # -(X - x2 Z) * yP ... (-yP) scalar
-        l3 = theta.mulfp(self.Pv, 0)
         l5 = X * y2 - x2 * Y
         if update:
             c = theta.sqr()
@@ -106,18 +109,112 @@ class _Pair:
             self.X = lam * h
             self.Y = theta * (g - h) - e * Y
             self.Z = Z * e
-        return l2, l3, l5
+        return lam, theta, l5
+
+    # ---- the Miller loop's view: one line per step, evaluated at P
+    def eval_tangent(self, c):
+        return c[0].mulfp(self.Pv, 1), c[1].mulfp(self.Pn, 0), c[2]     # xi 2YZ * yP,  xi X^2 * (-3 xP),  l0
+
+    def eval_chord(self, c):
+        return c[0].mulfp(self.Pm, 1), c[1].mulfp(self.Pv, 0), c[2]     # (X - x2 Z) * (-yP),  (Y - y2 Z) * xP,  l5
+
+    def double_step(self):
+        return self.eval_tangent(self.tangent_coeffs())
+
+    def add_step(self, x2, y2, update=True):
+        return self.eval_chord(self.chord_coeffs(x2, y2, update))
+
+    def add_q(self, sign):
+        """chord through R and +-Q, R <- R +- Q (miller_loop_native.rs:160-168)"""
+        return self.add_step(self.Qx, self.Qy if sign == 1 else self.neg_qy())
+
+    def frobenius_coeffs(self):
+        """the two Frobenius endpoints (:176-187, :266-280): chords through pi(Q) and -pi^2(Q)"""
+        b = self.b
+        q1x = b.const(_C2) * self.Qx.conj()
+        q1y = b.const(_C3) * self.Qy.conj()
+        c1 = self.chord_coeffs(q1x, q1y)
+        q2x = b.const(_C2) * q1x.conj()
+        nq2y = -(b.const(_C3) * q1y.conj())
+        c2 = self.chord_coeffs(q2x, nq2y, update=False)
+        return c1, c2
+
+    def frobenius_steps(self):
+        """the same two chords, each evaluated as soon as it exists (keeps the live program's instruction order)"""
+        b = self.b
+        q1x = b.const(_C2) * self.Qx.conj()
+        q1y = b.const(_C3) * self.Qy.conj()
+        yield self.add_step(q1x, q1y)
+        q2x = b.const(_C2) * q1x.conj()
+        nq2y = -(b.const(_C3) * q1y.conj())
+        yield self.add_step(q2x, nq2y, update=False)
 
 
-def _miller_core(b, n_pairs, track_scale):
+def line_schedule():
+    """The lines of one Miller loop in order: 'T' tangent, +1 / -1 chord through +-Q, 'F' the two Frobenius chords -
+    the order in which g2_prepare stores coefficient triples and a prepared pair reads them."""
+    naf = SIX_U_PLUS_2_NAF
+    top = len(naf) - 1
+    while naf[top] == 0:
+        top -= 1
+    out = ["T"]
+    for i in range(top - 1, -1, -1):
+        if i != top - 1:
+            out.append("T")
+        if naf[i]:
+            out.append(naf[i])
+    return out + ["F", "F"]
+
+
+PREP_LINES = len(line_schedule())       # coefficient triples per prepared G2 point
+PREP_FQ = PREP_LINES * 6                # Fq elements per prepared G2 point (include/bnp.h: BNP_PREP_FQ)
+
+
+class _PreparedPair:
+    """A pair whose G2 side arrives as line coefficients (program g2_prepare, the engine's `G2Prepared`): no point
+    arithmetic, every step is three loads and two Fq-scalar products."""
+
+    def __init__(self, b, pair_index, prep_index):
+        k = pair_index
+        self.b = b
+        self.Pv = b.ldg(isa.ARR_G1, 2 * k, 2 * k + 1)
+        self.Pn = -b.times(self.Pv, 3)
+        self.Pm = -self.Pv
+        self.base = prep_index * PREP_FQ
+        self.line = 0
+        self.Z = None
+
+    def _next(self):
+        f = self.base + 6 * self.line
+        self.line += 1
+        return tuple(self.b.ldg(isa.ARR_AUX, f + 2 * j, f + 2 * j + 1) for j in range(3))
+
+    eval_tangent = _Pair.eval_tangent
+    eval_chord = _Pair.eval_chord
+
+    def double_step(self):
+        return self.eval_tangent(self._next())
+
+    def add_q(self, sign):
+        return self.eval_chord(self._next())
+
+    def frobenius_steps(self):
+        yield self.eval_chord(self._next())
+        yield self.eval_chord(self._next())
+
+
+def _miller_core(b, n_pairs, track_scale, pairs=None):
     """Shared-squaring Miller loop over n_pairs pairs (n_pairs = 1 is miller_loop_BN_native).
-    Returns (g, S, exp_xi, exp_w): g = f_ref * S * xi^exp_xi * w^-exp_w  with S in Fq2 (None when untracked)."""
+    Returns (g, S, exp_xi, exp_w): g = f_ref * S * xi^exp_xi * w^-exp_w  with S in Fq2 (None when untracked).
+    `pairs`: pair objects (live `_Pair`s or `_PreparedPair`s); default: n_pairs live pairs."""
     naf = SIX_U_PLUS_2_NAF
     top = len(naf) - 1
     while naf[top] == 0:
         top -= 1
     assert naf[top] == 1  # multi_miller_loop_BN_native asserts this (:201); R starts at +Q
-    pairs = [_Pair(b, k) for k in range(n_pairs)]
+    if pairs is None:
+        pairs = [_Pair(b, k) for k in range(n_pairs)]
+    assert not track_scale or all(isinstance(pr, _Pair) for pr in pairs)
 
     exp_xi, exp_w = 0, 0
     S = None
@@ -166,9 +263,8 @@ def _miller_core(b, n_pairs, track_scale):
         first = False
         if naf[i] != 0:
             for pr in pairs:
-                y2 = pr.Qy if naf[i] == 1 else pr.neg_qy()
                 scale_chord(pr)
-                e0, e1, e3 = pr.add_step(pr.Qx, y2)
+                e0, e1, e3 = pr.add_q(naf[i])
                 exp_w += 2
                 g = b.fq12_mul_034(g, e0, e1, e3)
         if i == 0:
@@ -177,18 +273,24 @@ def _miller_core(b, n_pairs, track_scale):
 
     # Frobenius endpoints (:176-187, :266-280)
     for pr in pairs:
-        q1x = b.const(_C2) * pr.Qx.conj()
-        q1y = b.const(_C3) * pr.Qy.conj()
-        scale_chord(pr)
-        e0, e1, e3 = pr.add_step(q1x, q1y)
-        exp_w += 2
-        g = b.fq12_mul_034(g, e0, e1, e3)
-        q2x = b.const(_C2) * q1x.conj()
-        nq2y = -(b.const(_C3) * q1y.conj())
-        scale_chord(pr)
-        e0, e1, e3 = pr.add_step(q2x, nq2y, update=False)
-        exp_w += 2
-        g = b.fq12_mul_034(g, e0, e1, e3)
+        if track_scale:
+            # the scale of the first chord is Z before it, of the second Z after it
+            q1x = b.const(_C2) * pr.Qx.conj()
+            q1y = b.const(_C3) * pr.Qy.conj()
+            scale_chord(pr)
+            e0, e1, e3 = pr.add_step(q1x, q1y)
+            exp_w += 2
+            g = b.fq12_mul_034(g, e0, e1, e3)
+            q2x = b.const(_C2) * q1x.conj()
+            nq2y = -(b.const(_C3) * q1y.conj())
+            scale_chord(pr)
+            e0, e1, e3 = pr.add_step(q2x, nq2y, update=False)
+            exp_w += 2
+            g = b.fq12_mul_034(g, e0, e1, e3)
+        else:
+            for e0, e1, e3 in pr.frobenius_steps():
+                exp_w += 2
+                g = b.fq12_mul_034(g, e0, e1, e3)
     return g, S, exp_xi, exp_w
 
 
@@ -321,6 +423,42 @@ def prog_final_exp_witness(b):
 def prog_pairing(b, variant, n_pairs=1):
     """arr G1/G2 -> OUT: pairing.rs:20-22 fused in one launch (n_pairs > 1: product of pairings)."""
     g, _, _, _ = _miller_core(b, n_pairs, track_scale=False)
+    b.st_fq12(isa.ARR_OUT, _final_exp(b, g, variant))
+
+
+def prog_g2_prepare(b):
+    """arr G2 -> OUT[PREP_FQ Fq]: the line coefficients of one G2 point in `line_schedule()` order - the engine's
+    `G2Prepared` (SURVEY 8(f).2; ark-ec's `G2Prepared::from` builds the same list in its own normalisation)."""
+    pr = _Pair(b, 0, with_p=False)
+    line = 0
+
+    def put(c):
+        nonlocal line
+        for j in range(3):
+            b.stg(isa.ARR_OUT, 6 * line + 2 * j, 6 * line + 2 * j + 1, c[j])
+        line += 1
+
+    for n_done, step in enumerate(line_schedule()):
+        if step == "T":
+            if n_done:
+                b.cut()
+            put(pr.tangent_coeffs())
+        elif step == "F":
+            if line == PREP_LINES - 2:
+                c1, c2 = pr.frobenius_coeffs()
+                put(c1)
+                put(c2)
+        else:
+            put(pr.chord_coeffs(pr.Qx, pr.Qy if step == 1 else pr.neg_qy()))
+    assert line == PREP_LINES
+
+
+def prog_pairing_prepared(b, variant, kv, kp):
+    """arr G1 (kv + kp points), G2 (kv points), AUX (kp prepared points) -> OUT: the product of kv + kp pairings whose
+    last kp G2 points arrive as line coefficients - a Groth16 verifier's fixed verifying-key points: their point
+    arithmetic is done once, not once per proof."""
+    pairs = [_Pair(b, k) for k in range(kv)] + [_PreparedPair(b, kv + j, j) for j in range(kp)]
+    g, _, _, _ = _miller_core(b, kv + kp, track_scale=False, pairs=pairs)
     b.st_fq12(isa.ARR_OUT, _final_exp(b, g, variant))
 
 
@@ -530,6 +668,10 @@ def prog_opbench(b, op, count=2048):
     b.st_fq12(isa.ARR_OUT, vals)
 
 
+# (pairs with a live G2 point, pairs with a prepared one): a single prepared pairing, and the Groth16 shape
+# e(A, B) e(L, gamma) e(C, delta) e(alpha, beta) with B per proof and gamma, delta, beta from the verifying key
+PREPARED_SHAPES = [(0, 1), (1, 2), (1, 3)]
+
 PROGRAMS = [
     # (name, build function, kwargs)
     ("miller", prog_miller, {}),
@@ -549,7 +691,10 @@ PROGRAMS = [
 ] + [("opbench_" + o.lower(), prog_opbench, {"op": o}) for o in ("MUL", "SQR", "MULFP", "ADD", "SUB", "DBL", "NEG", "MULXI", "LIN4", "LIN4XI", "MULS", "MIX")] \
   + [("frobenius_%d" % k, prog_frobenius, {"power": k}) for k in range(12)] \
   + [("miller_x%d" % k, prog_miller, {"n_pairs": k}) for k in (2, 3, 4)] \
-  + [("pairing_x%d_v%d" % (k, v), prog_pairing, {"variant": v, "n_pairs": k}) for k in (2, 3, 4) for v in (0, 1)]
+  + [("pairing_x%d_v%d" % (k, v), prog_pairing, {"variant": v, "n_pairs": k}) for k in (2, 3, 4) for v in (0, 1)] \
+  + [("g2_prepare", prog_g2_prepare, {})] \
+  + [("pairing_p%d_%d_v%d" % (kv, kp, v), prog_pairing_prepared, {"variant": v, "kv": kv, "kp": kp})
+     for kv, kp in PREPARED_SHAPES for v in (0, 1)]
 
 
 def build_program(name, pool):

@@ -49,6 +49,9 @@ SIGNATURES = {
     "bnp_run_program_dev": (_int, [_int, ctypes.c_void_p, ctypes.c_char_p, _u64p, _u64p, _u64p, _u64p, _u64p, _sz]),
     "bnp_set_launch_config": (_int, [_int, _int]),
     "bnp_threads_per_block": (_int, []),
+    "bnp_g2_prepare_batch": (_int, [_u64p, _u64p, _sz]),
+    "bnp_pairing_prepared_batch": (_int, [_u64p, _u64p, _u64p, _u64p, _sz, _int, _int, _int]),
+    "bnp_pairing_prepared_dev": (_int, [_int, ctypes.c_void_p, _u64p, _u64p, _u64p, _u64p, _sz, _int, _int, _int]),
     "bnp_decode_g1_batch": (_int, [_int, ctypes.c_void_p, _sz, _u64p, ctypes.c_void_p]),
     "bnp_decode_g2_batch": (_int, [_int, ctypes.c_void_p, _sz, _u64p, ctypes.c_void_p, _int]),
     "bnp_encode_fq12_batch": (_int, [_u64p, _sz, ctypes.c_void_p]),

@@ -248,3 +248,25 @@ def test_validation_programs():
                     assert got[:6] == [0] * 6
                     return
     raise AssertionError("no twist point found")
+
+
+def test_prepared_g2_programs():
+    """g2_prepare's line coefficients fed to the prepared-pair programs give the same values as the
+    programs that do the point arithmetic themselves (a single pairing, and the Groth16 shape 1 live + 3 prepared)."""
+    coeffs = []
+    for _, q in PTS[:4]:
+        got, _ = run("g2_prepare", {isa.ARR_G2: [q[0][0], q[0][1], q[1][0], q[1][1]]}, 18)
+        assert len(got) == programs.PREP_FQ
+        coeffs.append(got)
+    p, q = PTS[0]
+    got, _ = run("pairing_p0_1_v0", {isa.ARR_G1: [p[0], p[1]], isa.ARR_AUX: coeffs[0]}, 18)
+    assert got == O.pairing(p, q)
+    # 1 live + 3 prepared = the product of four pairings
+    arrays = g1g2(PTS[:4])
+    arrays[isa.ARR_G2] = arrays[isa.ARR_G2][:4]
+    arrays[isa.ARR_AUX] = coeffs[1] + coeffs[2] + coeffs[3]
+    want = O.final_exp_native(O.multi_miller_loop_native(PTS[:4]))
+    got, _ = run("pairing_p1_3_v0", arrays, 18)
+    assert got == want
+    got, _ = run("pairing_p1_3_v1", arrays, 18)
+    assert got == O.final_exp_ark(O.multi_miller_loop_native(PTS[:4]))
