@@ -10,6 +10,8 @@ Tower (identical to the reference's `MyFq12`, /root/reference/src/miller_loop_na
     Fq12 = Fq2[w]/(w^6 - xi);  a 12-element value is a list of six Fq2 SSA values [a0..a5] (w^0..w^5).
     Internally A = (a0,a2,a4), B = (a1,a3,a5) are its Fq6 = Fq2[v]/(v^3-xi) halves, v = w^2.
 """
+import os
+
 from . import isa
 
 P = 0x30644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD47
@@ -349,23 +351,53 @@ class Builder:
         n5 = three_plus_two(b1, f[5])
         return [n0, n1, n2, n3, n4, n5]
 
-    def fq12_pow_x_cyclo(self, m):
-        """m^BN_X for cyclotomic m, same NAF walk as pow_native (final_exp_native.rs:56-84) with the
-        division by `a` replaced by a multiplication by conj(a) = a^-1 (valid after the easy part)."""
-        naf = naf_digits(BN_X)
-        res = m
-        started = False
-        for z in reversed(naf):
-            if started:
+    def fq12_pow_x_cyclo(self, m, window=None):
+        """m^BN_X for cyclotomic m.  The reference walks the NAF of the exponent (pow_native, final_exp_native.rs:56-84:
+        62 squarings, 23 multiplications / divisions); m^BN_X is one well-defined group element, so any addition chain
+        gives the same bits, and in the cyclotomic subgroup (after the easy part) squarings are Granger-Scott and an
+        inverse is a conjugation.  Here: width-4 signed windows - digits +-1, +-3, +-5, +-7 on a table m, m^3, m^5, m^7
+        (one squaring and three multiplications to build) - 13 multiplications in the walk instead of 23:
+        16 Fq12 multiplications per exponentiation instead of 23 (-6 % of a pairing's MACs).  window=2 is the
+        reference's NAF walk."""
+        if window is None:
+            window = int(os.environ.get("BNP_POWX_WINDOW", "4"))
+        digits = wnaf_digits(BN_X, window)
+        table = {1: m}
+        top = max(abs(z) for z in digits)
+        if top > 1:
+            m2 = self.fq12_cyclo_sqr(m)
+            for k in range(3, top + 1, 2):
+                table[k] = self.fq12_mul(table[k - 2], m2)
+        res = None
+        for z in reversed(digits):
+            if res is not None:
                 self.cut()
                 res = self.fq12_cyclo_sqr(res)
             if z != 0:
-                if started:
-                    res = self.fq12_mul(res, m) if z == 1 else self.fq12_mul_conj(res, m)
+                t = table[abs(z)]
+                if res is None:
+                    assert z > 0
+                    res = t
                 else:
-                    assert z == 1
-                    started = True
+                    res = self.fq12_mul(res, t) if z > 0 else self.fq12_mul_conj(res, t)
         return res
+
+
+def wnaf_digits(e, w):
+    """LSB-first width-w non-adjacent form of a positive integer: odd digits in (-2^(w-1), 2^(w-1)), at most one non-zero
+    digit in any w consecutive positions (w = 2 is the NAF of get_naf, final_exp_native.rs:86-128)."""
+    out = []
+    while e:
+        if e & 1:
+            z = e % (1 << w)
+            if z >= 1 << (w - 1):
+                z -= 1 << w
+            e -= z
+        else:
+            z = 0
+        out.append(z)
+        e >>= 1
+    return out
 
 
 def naf_digits(e):

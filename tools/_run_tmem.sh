@@ -5,6 +5,8 @@ b() { # name, env...
   echo "$name : $r" | tee -a gpurun_out/tmem_results.txt
 }
 echo "--- $(date)" >> gpurun_out/tmem_results.txt
+if [ -n "$MAIN" ]; then b main; fi
 for v in ${VARIANTS}; do
   b $v BNP_LIB=$PWD/build_var/$v.so
 done
+if [ -n "$MAIN" ]; then b main_again; fi
