@@ -270,3 +270,16 @@ def test_prepared_g2_programs():
     assert got == want
     got, _ = run("pairing_p1_3_v1", arrays, 18)
     assert got == O.final_exp_ark(O.multi_miller_loop_native(PTS[:4]))
+
+
+def test_windowed_exponent_digits():
+    """builder.wnaf_digits: the digits the hard part's m^x walks (width 4) rebuild BN_X, are odd and below 8, keep at
+    least three zeros between non-zero digits, and width 2 is the reference's NAF (get_naf, final_exp_native.rs:86-128)."""
+    from plonky2_bn254_pairing_b200.microcode.builder import BN_X, wnaf_digits
+
+    d = wnaf_digits(BN_X, 4)
+    assert sum(z << i for i, z in enumerate(d)) == BN_X
+    nz = [i for i, z in enumerate(d) if z]
+    assert all(d[i] % 2 and abs(d[i]) < 8 for i in nz) and all(b - a >= 4 for a, b in zip(nz, nz[1:]))
+    assert d[-1] > 0 and len(nz) == 14
+    assert wnaf_digits(BN_X, 2) == naf_digits(BN_X) == [int(z) for z in O.get_naf([BN_X])][:len(naf_digits(BN_X))]
