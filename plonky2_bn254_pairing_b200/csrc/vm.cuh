@@ -58,6 +58,9 @@ __device__ __constant__ u32 BNP_CONSTS[BNP_MAX_CONST][16];
 // per access, 8 % of the kernel; profiles/experiments_r2.txt).  One 384-thread block per SM then holds 18 slots per
 // pairing instead of 9, and a fused pairing shrinks from 18 400 to 9 300 sequencer instructions (spills and re-loads
 // from 9 600 to 1 000); a 512-thread block holds 14 slots at 16 warps per SM.
+#ifndef BNP_UNIFORM_DECODE
+#define BNP_UNIFORM_DECODE 1
+#endif
 #ifndef BNP_LIN_PREFETCH
 #define BNP_LIN_PREFETCH 0
 #endif
@@ -160,9 +163,14 @@ __device__ __forceinline__ void stg_fp(u64* arr, u32 f, u32 n, u32 e, const u32*
 // fetched one iteration ahead of its use (the loop is software-pipelined by hand); multiplier 0 pads the shorter
 // list.  Every test below is warp-uniform.
 // ---------------------------------------------------------------------------------------------
+#if BNP_UNIFORM_DECODE
+#define BNP_UNI(x) __reduce_or_sync(0xffffffffu, (x))
+#else
+#define BNP_UNI(x) (x)
+#endif
 #define BNP_LIN_FETCH(J, ZA, ZB, TT)                                          \
     {                                                                         \
-        TT = __ldg(ents + (J));                                               \
+        TT = BNP_UNI(__ldg(ents + (J)));                                      \
         S.issue_half(ZA, TT & 0xffu, (TT >> 8) & 1u);                         \
         S.issue_half(ZB, (TT >> 16) & 0xffu, (TT >> 24) & 1u);                \
         S.wait_half(ZA);                                                      \
@@ -343,7 +351,11 @@ __device__ __forceinline__ void vm_product(const Slots<T>& S, u32 op, const u64*
     u32 np = 0, d2 = 0;  // np: entry pairs of the post LIN
     bool store_r = true;
     if (imm & BNP_MUL_EXT) {
+#if BNP_UNIFORM_DECODE
+        const u32 xl = __reduce_or_sync(0xffffffffu, (u32)w0), xh = __reduce_or_sync(0xffffffffu, (u32)(w0 >> 32));
+#else
         const u32 xl = (u32)w0, xh = (u32)(w0 >> 32);
+#endif
         d2 = xl & 0xffu;
         const u32 hflags = xh & 0xffu;
         np = (xh >> 8) & 0xffu;
@@ -430,6 +442,9 @@ __global__ void __launch_bounds__(T, (BNP_MINB * 64) / T > 0 ? (BNP_MINB * 64) /
     {
         const u32 warp = threadIdx.x >> 5;
         S.tbase = tmem_base + (((warp & 3u) * 32u) << 16) + (warp >> 2) * args.tmem_cols_per_warp;
+#if BNP_UNIFORM_DECODE
+        S.tbase = __reduce_or_sync(0xffffffffu, S.tbase);  // the same in every lane: keep it in a uniform register
+#endif
     }
     const u32 total = gridDim.x * T;
     const u32 gtid = blockIdx.x * T + threadIdx.x;
@@ -471,7 +486,14 @@ __global__ void __launch_bounds__(T, (BNP_MINB * 64) / T > 0 ? (BNP_MINB * 64) /
         u64 ins = __ldg(pc++);
         bool running = true;
         while (running) {
+#if BNP_UNIFORM_DECODE
+            // Every lane holds the same instruction word, but the compiler cannot know: a warp-wide OR (REDUX) returns it in
+            // a UNIFORM register, so that field extraction runs on the uniform datapath, branches on instruction fields
+            // need no reconvergence barriers (BSSY / BSYNC) and tensor-memory addresses need no R2UR.
+            const u32 lo = __reduce_or_sync(0xffffffffu, (u32)ins), hi = __reduce_or_sync(0xffffffffu, (u32)(ins >> 32));
+#else
             const u32 lo = (u32)ins, hi = (u32)(ins >> 32);
+#endif
             const u32 op = lo & 0xffu, d = (lo >> 8) & 0xffu, a = (lo >> 16) & 0xffu, b = lo >> 24;
             const u32 c = hi & 0xffu, ee = (hi >> 8) & 0xffu, imm = hi >> 16;
             // the word after the instruction: its extension word, its first entry word, or the next instruction
