@@ -815,6 +815,9 @@ int bnp_pairing_product(const uint64_t* g1, const uint64_t* g2, uint64_t* out, s
         if (g_ctx[d].dev == c0.dev) {
             CK(cudaMemcpy2DAsync(c0.stage[4] + slot, nparts * 8, partial[d], 8, 8, 48, cudaMemcpyDeviceToDevice, c0.stream));
         } else {
+            // c0.stage[2] doubles as the bounce buffer and as device 0's own partial: the asynchronous copy that
+            // reads it above must have finished before a peer copy overwrites it
+            CK(cudaStreamSynchronize(c0.stream));
             CK(cudaMemcpyPeer(c0.stage[2], c0.dev, partial[d], g_ctx[d].dev, 384));
             CK(cudaMemcpy2DAsync(c0.stage[4] + slot, nparts * 8, c0.stage[2], 8, 8, 48, cudaMemcpyDeviceToDevice, c0.stream));
             CK(cudaStreamSynchronize(c0.stream));
