@@ -10,6 +10,7 @@ pub const BNP_WIRE_EIP197: c_int = 2;
 pub const BNP_POINT_OK: u8 = 0;
 pub const BNP_POINT_INFINITY: u8 = 1;
 pub const BNP_EMALFORMED: c_int = -6;
+pub const BNP_PREP_FQ: usize = 546;
 
 extern "C" {
     pub fn bnp_init(devices: *const c_int, n_devices: c_int) -> c_int;
@@ -28,6 +29,10 @@ extern "C" {
     pub fn bnp_fq12_mul_batch(a: *const u64, b: *const u64, out: *mut u64, n: usize) -> c_int;
     /// pow_native (final_exp_native.rs:56): `exp` = n_limbs little-endian u64 limbs shared by the batch
     pub fn bnp_pow_u64_batch(input: *const u64, out: *mut u64, n: usize, exp: *const u64, n_limbs: usize) -> c_int;
+    /// prepared G2 points (include/bnp.h): BNP_PREP_FQ Fq of line coefficients per point
+    pub fn bnp_g2_prepare_batch(g2: *const u64, coeffs: *mut u64, n: usize) -> c_int;
+    pub fn bnp_pairing_prepared_batch(g1: *const u64, g2: *const u64, prepared: *const u64, out: *mut u64, n: usize,
+                                      kv: c_int, kp: c_int, variant: c_int) -> c_int;
     /// wire formats (include/bnp.h): bytes -> SoA + one status byte per element, decoded on the device
     pub fn bnp_decode_g1_batch(fmt: c_int, input: *const u8, n: usize, g1: *mut u64, status: *mut u8) -> c_int;
     pub fn bnp_decode_g2_batch(fmt: c_int, input: *const u8, n: usize, g2: *mut u64, status: *mut u8, check_subgroup: c_int) -> c_int;

@@ -337,3 +337,49 @@ pub fn eip197_pairing_check(input: &[u8]) -> Option<bool> {
     check(rc);
     Some(res == 1)
 }
+
+// ---- prepared G2 points ------------------------------------------------------
+/// The engine's `G2Prepared`: the line coefficients of fixed G2 points (a Groth16 verifying key's beta, gamma, delta),
+/// computed once on the GPU and shared by every proof of a batch.  Layout `[kp * BNP_PREP_FQ][4][1]` u64.
+pub struct PreparedG2 {
+    coeffs: Vec<u64>,
+    kp: usize,
+}
+
+pub fn prepare_g2(qs: &[G2Affine]) -> PreparedG2 {
+    init();
+    let kp = qs.len();
+    let mut per_point = vec![0u64; ffi::BNP_PREP_FQ * 4 * kp];           // [BNP_PREP_FQ][4][kp]
+    check(unsafe { ffi::bnp_g2_prepare_batch(pack_g2(qs).as_ptr(), per_point.as_mut_ptr(), kp) });
+    let mut coeffs = vec![0u64; ffi::BNP_PREP_FQ * 4 * kp];              // [kp * BNP_PREP_FQ][4][1]
+    for j in 0..kp {
+        for row in 0..ffi::BNP_PREP_FQ * 4 {
+            coeffs[j * ffi::BNP_PREP_FQ * 4 + row] = per_point[row * kp + j];
+        }
+    }
+    PreparedG2 { coeffs, kp }
+}
+
+/// out[i] = final_exp( e-Miller(ps_live[i], qs_live[i]) * prod_j e-Miller(ps_fixed[i][j], key.point[j]) ): one live pair and
+/// `key.kp` (2 or 3) prepared pairs per proof - the Groth16 verification equation with the key prepared once.
+pub fn groth16_shaped_batch(ps_live: &[G1Affine], qs_live: &[G2Affine], ps_fixed: &[Vec<G1Affine>], key: &PreparedG2) -> Vec<Fq12> {
+    let n = ps_live.len();
+    assert!(qs_live.len() == n && ps_fixed.len() == n && ps_fixed.iter().all(|v| v.len() == key.kp));
+    init();
+    let k = 1 + key.kp;
+    let mut g1 = vec![0u64; 8 * k * n];
+    for e in 0..n {
+        put(&mut g1, 0, n, e, &ps_live[e].x);
+        put(&mut g1, 1, n, e, &ps_live[e].y);
+        for j in 0..key.kp {
+            put(&mut g1, 2 * (j + 1), n, e, &ps_fixed[e][j].x);
+            put(&mut g1, 2 * (j + 1) + 1, n, e, &ps_fixed[e][j].y);
+        }
+    }
+    let mut out = vec![0u64; 48 * n];
+    check(unsafe {
+        ffi::bnp_pairing_prepared_batch(g1.as_ptr(), pack_g2(qs_live).as_ptr(), key.coeffs.as_ptr(), out.as_mut_ptr(), n, 1,
+                                        key.kp as i32, ffi::BNP_VARIANT_REFERENCE)
+    });
+    unpack_fq12(&out, n).into_iter().map(|f| f.into()).collect()
+}
