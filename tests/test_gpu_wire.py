@@ -133,3 +133,17 @@ def test_eip197_precompile(lib):
             api.eip197_pairing_check(bad)
     with pytest.raises(native.BnpError):
         api.eip197_pairing_check(bytes(100))
+
+
+@pytest.mark.parametrize("n", [1, 33, 1000])
+def test_compressed_decode_at_size(lib, n):
+    """ragged and larger batches of compressed points (every point needs its square root): coordinates against the
+    oracle's decoder, then the decoded batch through the fused pairing against the C oracle"""
+    Ps, Qs = point_pool(64)
+    idx = np.arange(n)
+    ps = [Ps[i % 64] if i % 3 else _neg1(Ps[i % 64]) for i in idx]
+    qs = [Qs[(5 * i + 1) % 64] if i % 2 else _neg2(Qs[(5 * i + 1) % 64]) for i in idx]
+    g1, s1 = api.decode_g1_soa(W.COMPRESSED, b"".join(W.encode_g1(p, W.COMPRESSED) for p in ps))
+    g2, s2 = api.decode_g2_soa(W.COMPRESSED, b"".join(W.encode_g2(q, W.COMPRESSED) for q in qs), check_subgroup=(n <= 33))
+    assert not s1.any() and not s2.any()
+    assert np.array_equal(g1, api.pack_soa(api.g1_rows(ps))) and np.array_equal(g2, api.pack_soa(api.g2_rows(qs)))
