@@ -453,6 +453,35 @@ def run_extras(rig, peak, args):
     if not same:
         return extra, False
 
+    # ---- wire formats: 2^16 compressed ark points decoded on the device (host bytes in, SoA out; the
+    # G2 half includes one Fq2 square root and the subgroup test per point), checked against the points they encode
+    okw = True
+    if rank == 0:
+        import time as _time
+
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import wire_formats as W
+
+        nw = 1 << 16
+        g1w, g2w, _ = wl.pairing_inputs(nw, K=POOL_K, offset=(7 << 24))
+        pts1, pts2 = api.unpack_soa(g1w[:, :, :256]), api.unpack_soa(g2w[:, :, :256])
+        b1 = b"".join(W.encode_g1((r[0], r[1]), W.COMPRESSED) for r in pts1) * (nw // 256)
+        b2 = b"".join(W.encode_g2(((r[0], r[1]), (r[2], r[3])), W.COMPRESSED) for r in pts2) * (nw // 256)
+        api.decode_g1_soa(W.COMPRESSED, b1[:32 * 256])
+        t0 = _time.perf_counter()
+        d1, s1 = api.decode_g1_soa(W.COMPRESSED, b1)
+        t1 = _time.perf_counter()
+        d2, s2 = api.decode_g2_soa(W.COMPRESSED, b2, check_subgroup=True)
+        t2 = _time.perf_counter()
+        okw = (not s1.any() and not s2.any() and np.array_equal(d1[:, :, :256], g1w[:, :, :256])
+               and np.array_equal(d2[:, :, :256], g2w[:, :, :256]) and np.array_equal(d2[:, :, -256:], g2w[:, :, :256]))
+        extra["wire_decode_2e16"] = {
+            "g1_compressed_points_per_s": nw / (t1 - t0), "g2_compressed_with_subgroup_check_points_per_s": nw / (t2 - t1),
+            "api": "bnp_decode_g1_batch / bnp_decode_g2_batch (host pointers, copies and status bytes included)",
+            "equal_to_the_encoded_points": bool(okw)}
+    if not rig.all_ok(bool(okw)):
+        return extra, False
+
     # ---- the one real exchange step: ONE product over 2^20 pairs, sharded by index range over the ranks
     from plonky2_bn254_pairing_b200 import sharding
     from plonky2_bn254_pairing_b200 import workload as wl
