@@ -83,6 +83,14 @@ struct Slots {
     // tcgen05.wait::ld.  `wait*` carries the real wait instruction for every TMEM load issued so far; `dep*` emits
     // nothing and only ties further registers to the statement order (volatile statements keep their order), so that
     // no use of them is scheduled before the wait.
+    // one Fq by its index h = 2 * slot + half (the form LIN entries carry): one multiplication per address
+    __device__ __forceinline__ void issue_fq(u32* r, u32 h) const {
+        const uint4 q = base[h * T];
+        r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w;
+        asm volatile(BNP_ST_WAIT_PREFIX "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(tbase + h * 4u));
+    }
     __device__ __forceinline__ void issue_half(u32* r, u32 s, u32 half) const {
         const uint4 q = base[s * (2 * T) + half * T];
         r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w;
@@ -158,7 +166,7 @@ __device__ __forceinline__ void stg_fp(u64* arr, u32 f, u32 n, u32 e, const u32*
 // ---------------------------------------------------------------------------------------------
 // LIN engine:  out_c = sum_j mult_j * (neg_j ? p - z_j : z_j)  <  1024 p  for c = 0, 1, each reduced once by a
 // quotient estimate.  An entry is one pair of 4-deep IMAD.WIDE chains into 64-bit-column accumulators (E: even limb
-// positions, O: odd).  Entries are 16 bits, [slot:8][half:1][neg:1][mult:6], and come in (component 0, component 1)
+// positions, O: odd).  Entries are 16 bits, [2 * slot + half : 9][neg:1][mult:6], and come in (component 0, component 1)
 // pairs, one pair per 32-bit word; the two components are independent chains the scheduler interleaves.  A pair is
 // fetched one iteration ahead of its use (the loop is software-pipelined by hand); multiplier 0 pads the shorter
 // list.  Every test below is warp-uniform.
@@ -171,8 +179,8 @@ __device__ __forceinline__ void stg_fp(u64* arr, u32 f, u32 n, u32 e, const u32*
 #define BNP_LIN_FETCH(J, ZA, ZB, TT)                                          \
     {                                                                         \
         TT = BNP_UNI(__ldg(ents + (J)));                                      \
-        S.issue_half(ZA, TT & 0xffu, (TT >> 8) & 1u);                         \
-        S.issue_half(ZB, (TT >> 16) & 0xffu, (TT >> 24) & 1u);                \
+        S.issue_fq(ZA, TT & 0x1ffu);                                          \
+        S.issue_fq(ZB, (TT >> 16) & 0x1ffu);                                  \
         S.wait_half(ZA);                                                      \
         S.dep_half(ZB);                                                       \
     }

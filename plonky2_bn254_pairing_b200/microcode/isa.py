@@ -37,7 +37,7 @@ LIN is the general linear instruction: each of the two output components is a la
 (this subsumes add, sub, neg, double, conj, multiplication by xi = 9 + u and by small constants), reduced once by a
 quotient estimate.  Every entry is one 8-MAC IMAD.WIDE chain into a 64-bit-column accumulator - the accumulation
 costs no ALU instructions.  Entries come in (component 0, component 1) pairs; header word: d, a = number of pairs;
-entries follow, two pairs per word: [slot:8][half:1][neg:1][mult:6].
+entries follow, two pairs per word: [2 * slot + half : 9][neg:1][mult:6].
 
 `emit_c_defines()` writes the opcode numbers into the generated header so the CUDA side cannot drift.
 """
@@ -119,12 +119,14 @@ def decode_ext(w):
 
 # LIN entry (16 bits): out_component += (neg ? p - z : z) * mult,  z = half `half` (0: c0, 1: c1) of slot `slot`
 def encode_entry(slot, half, mult, neg):
+    """bits 0-8: 2 * slot + half - the index of the Fq the entry reads, so that the kernel gets both of its addresses
+    (shared memory: index * T uint4, tensor memory: index * 4 columns) with one multiplication each."""
     assert 0 <= slot <= 0xFF and half in (0, 1) and 0 <= mult <= LIN_MAX_MULT
-    return slot | (half << 8) | ((1 if neg else 0) << 9) | (mult << 10)
+    return (2 * slot + half) | ((1 if neg else 0) << 9) | (mult << 10)
 
 
 def decode_entry(t):
-    return (t & 0xFF, (t >> 8) & 1, (t >> 10) & 63, bool((t >> 9) & 1))
+    return ((t & 0x1FF) >> 1, t & 1, (t >> 10) & 63, bool((t >> 9) & 1))
 
 
 def pair_entries(ent0, ent1, pad_slot):
