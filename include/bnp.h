@@ -93,6 +93,15 @@ int bnp_pow_u64_batch(const uint64_t* in, uint64_t* out, size_t n, const uint64_
  * on whatever coordinates they are given.  g1 or g2 may be NULL (only the other group is checked); coordinates
  * (0, 0) - ark's encoding of the identity, which carries a separate flag there - are reported as invalid. */
 int bnp_validate_batch(const uint64_t* g1 /* [2][4][n] */, const uint64_t* g2 /* [4][4][n] */, unsigned char* ok /* [n] */, size_t n);
+/* Scalar multiplication on the device: out[e] = scalars[e] * pts[e] on G1 (group = 1, pts and out
+ * [2][4][n]) or G2 (group = 2, [4][4][n]) - what `G1Affine * Fr` / `G2Affine * Fr` compute in the reference's tests
+ * (miller_loop_native.rs:331-334) and what a verifier folding many pairing checks into one by a random linear
+ * combination needs in front of the pairing batch.  scalars: [4][n], each a PLAIN 256-bit integer in four little-endian
+ * 64-bit limbs (ark's `Fr::into_bigint()`), any value below 2^256.  inf[e] = 1 where the result is the point at
+ * infinity (its coordinates come back as (0, 0), ark's encoding); input coordinates (0, 0) are the point at infinity.
+ * The points are NOT validated (bnp_validate_batch does that): the group law is applied to whatever on-curve
+ * coordinates arrive. */
+int bnp_scalar_mul_batch(int group, const uint64_t* pts, const uint64_t* scalars, uint64_t* out, unsigned char* inf /* [n] */, size_t n);
 /* MyFq12 `Mul`: out = a * b element-wise. */
 int bnp_fq12_mul_batch(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
 
@@ -107,6 +116,8 @@ int bnp_pairing_dev(int device, void* stream, const uint64_t* g1, const uint64_t
 int bnp_frobenius_dev(int device, void* stream, const uint64_t* in, uint64_t* out, size_t n, size_t power);
 int bnp_pow_u64_dev(int device, void* stream, const uint64_t* in, uint64_t* out, size_t n, const uint64_t* exp, size_t n_limbs);
 int bnp_validate_dev(int device, void* stream, const uint64_t* g1, const uint64_t* g2, unsigned char* ok /* device, [n] */, size_t n);
+int bnp_scalar_mul_dev(int device, void* stream, int group, const uint64_t* pts, const uint64_t* scalars, uint64_t* out,
+                       unsigned char* inf /* device, [n] */, size_t n);
 int bnp_fq12_mul_dev(int device, void* stream, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
 /* In-place tree product of n MyFq12 values (buf[12][4][n], destroyed) -> out[12][4][1]. */
 int bnp_fq12_product_dev(int device, void* stream, uint64_t* buf, uint64_t* out, size_t n);

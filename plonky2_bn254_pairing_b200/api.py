@@ -164,6 +164,19 @@ def validate_soa(g1=None, g2=None):
     return ok
 
 
+def scalar_mul_soa(group, pts, scalars):
+    """group 1: pts uint64 [2][4][n] (G1), 2: [4][4][n] (G2); scalars uint64 [4][n], plain little-endian 256-bit
+    integers -> (points of the same shape, uint8 [n] infinity flags): out_i = scalars_i * pts_i."""
+    lib = native.lib()
+    n = pts.shape[2]
+    out = np.empty_like(pts)
+    inf = np.zeros(n, dtype=np.uint8)
+    sc = np.ascontiguousarray(scalars, dtype=np.uint64)
+    assert sc.shape == (4, n)
+    native.check(lib.bnp_scalar_mul_batch(group, _ptr(pts), _ptr(sc), _ptr(out), inf.ctypes.data_as(ctypes.c_void_p), n))
+    return out, inf
+
+
 # ----------------------------------------------------------------------------- prepared G2 points (SURVEY 8(f).2)
 PREP_FQ = 546
 
@@ -334,6 +347,35 @@ def validate_batch(Ps=None, Qs=None):
     if g1 is None and g2 is None:
         return []
     return [bool(v) for v in validate_soa(g1, g2)]
+
+
+def _scalar_rows(ks):
+    a = np.zeros((4, len(ks)), dtype=np.uint64)
+    for i, k in enumerate(ks):
+        assert 0 <= k < 1 << 256
+        for j in range(4):
+            a[j, i] = (k >> (64 * j)) & 0xFFFFFFFFFFFFFFFF
+    return a
+
+
+def g1_scalar_mul_batch(Ps, ks):
+    """[k_i * P_i] on G1 - `G1Affine * Fr` of the reference's tests (miller_loop_native.rs:333), batched.  Points are
+    (x, y) integer pairs; the point at infinity is None (in and out)."""
+    if not Ps:
+        return []
+    out, inf = scalar_mul_soa(1, pack_soa(g1_rows([p if p is not None else (0, 0) for p in Ps])), _scalar_rows(ks))
+    rows = unpack_soa(out)
+    return [None if f else (r[0], r[1]) for r, f in zip(rows, inf)]
+
+
+def g2_scalar_mul_batch(Qs, ks):
+    """[k_i * Q_i] on G2 (`G2Affine * Fr`, miller_loop_native.rs:334); points are ((x0, x1), (y0, y1)) or None."""
+    if not Qs:
+        return []
+    zero = ((0, 0), (0, 0))
+    out, inf = scalar_mul_soa(2, pack_soa(g2_rows([q if q is not None else zero for q in Qs])), _scalar_rows(ks))
+    rows = unpack_soa(out)
+    return [None if f else ((r[0], r[1]), (r[2], r[3])) for r, f in zip(rows, inf)]
 
 
 def frobenius_map_native_batch(fs, power):

@@ -19,6 +19,7 @@
 #include "microcode_tables.h"
 #include "vm.cuh"
 #include "wire.cuh"
+#include "scalar.cuh"
 
 // ok[e] = (first ? 1 : ok[e]) & (every limb of element e in the `rows` limb rows of `res` is zero)
 __global__ void bnp_zero_flags_kernel(const u64* res, u32 rows, size_t stride, size_t n, unsigned char* ok, int first) {
@@ -771,6 +772,46 @@ int bnp_validate_batch(const uint64_t* g1, const uint64_t* g2, unsigned char* ok
     return sync_all();
 }
 
+// out = scalars * pts on device arrays (csrc/scalar.cuh); group 1: G1 ([2][4][n]), 2: G2 ([4][4][n])
+static int scalar_mul_dev_locked(DevCtx& c, void* stream, int group, const u64* pts, const u64* scalars, u64* out,
+                                 unsigned char* inf, size_t n) {
+    cudaStream_t st = stream ? (cudaStream_t)stream : c.stream;
+    const unsigned blocks = (unsigned)((n + 127) / 128);
+    if (group == 1)
+        bnp_scalar_mul_kernel<Fp1><<<blocks, 128, 0, st>>>(pts, scalars, out, inf, n);
+    else
+        bnp_scalar_mul_kernel<Fp2><<<blocks, 128, 0, st>>>(pts, scalars, out, inf, n);
+    CK(cudaGetLastError());
+    g_launches++;
+    return BNP_OK;
+}
+
+int bnp_scalar_mul_batch(int group, const uint64_t* pts, const uint64_t* scalars, uint64_t* out, unsigned char* inf, size_t n) {
+    if (group != 1 && group != 2) return BNP_EINVAL;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_ctx.empty()) return BNP_ENODEV;
+    if (n == 0) return BNP_OK;
+    if (!pts || !scalars || !out || !inf) return BNP_EINVAL;
+    const size_t K = group == 1 ? 2 : 4;
+    auto parts = split_range(n, g_ctx.size());
+    for (size_t d = 0; d < g_ctx.size(); d++) {
+        if (parts[d].cnt == 0) continue;
+        DevCtx& c = g_ctx[d];
+        CK(cudaSetDevice(c.dev));
+        int rc;
+        const size_t cnt = parts[d].cnt;
+        if ((rc = copy_in(c, 1, pts, K, n, parts[d].off, cnt))) return rc;
+        if ((rc = copy_in(c, 0, scalars, 1, n, parts[d].off, cnt))) return rc;
+        if ((rc = ensure_stage(c, 3, K * 32 * cnt))) return rc;
+        if ((rc = ensure_stage(c, 5, cnt))) return rc;
+        unsigned char* flags = reinterpret_cast<unsigned char*>(c.stage[5]);
+        if ((rc = scalar_mul_dev_locked(c, nullptr, group, c.stage[1], c.stage[0], c.stage[3], flags, cnt))) return rc;
+        if ((rc = copy_out(c, 3, out, K, n, parts[d].off, cnt))) return rc;
+        CK(cudaMemcpyAsync(inf + parts[d].off, flags, cnt, cudaMemcpyDeviceToHost, c.stream));
+    }
+    return sync_all();
+}
+
 int bnp_fq12_mul_batch(const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
     return run_host("fq12_mul", {{2, a, 12}, {4, b, 12}}, out, 12, n);
 }
@@ -1045,6 +1086,16 @@ int bnp_validate_dev(int device, void* stream, const uint64_t* g1, const uint64_
     if (!ok) return BNP_EINVAL;
     CK(cudaSetDevice(c->dev));
     return validate_dev_locked(*c, stream, g1, g2, ok, n);
+}
+
+int bnp_scalar_mul_dev(int device, void* stream, int group, const uint64_t* pts, const uint64_t* scalars, uint64_t* out,
+                       unsigned char* inf, size_t n) {
+    DEV_PROLOGUE
+    if (group != 1 && group != 2) return BNP_EINVAL;
+    if (n == 0) return BNP_OK;
+    if (!pts || !scalars || !out || !inf) return BNP_EINVAL;
+    CK(cudaSetDevice(c->dev));
+    return scalar_mul_dev_locked(*c, stream, group, pts, scalars, out, inf, n);
 }
 
 int bnp_fq12_mul_dev(int device, void* stream, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {

@@ -31,6 +31,8 @@ SIGNATURES = {
     "bnp_fq12_mul_batch": (_int, [_u64p, _u64p, _u64p, _sz]),
     "bnp_validate_batch": (_int, [_u64p, _u64p, ctypes.c_void_p, _sz]),
     "bnp_validate_dev": (_int, [_int, ctypes.c_void_p, _u64p, _u64p, ctypes.c_void_p, _sz]),
+    "bnp_scalar_mul_batch": (_int, [_int, _u64p, _u64p, _u64p, ctypes.c_void_p, _sz]),
+    "bnp_scalar_mul_dev": (_int, [_int, ctypes.c_void_p, _int, _u64p, _u64p, _u64p, ctypes.c_void_p, _sz]),
     "bnp_pow_u64_batch": (_int, [_u64p, _u64p, _sz, _u64p, _sz]),
     "bnp_pow_u64_dev": (_int, [_int, ctypes.c_void_p, _u64p, _u64p, _sz, _u64p, _sz]),
     "bnp_miller_loop_dev": (_int, [_int, ctypes.c_void_p, _u64p, _u64p, _u64p, _sz, _int]),

@@ -38,6 +38,8 @@ extern "C" {
     pub fn bnp_decode_g2_batch(fmt: c_int, input: *const u8, n: usize, g2: *mut u64, status: *mut u8, check_subgroup: c_int) -> c_int;
     pub fn bnp_encode_fq12_batch(f12: *const u64, n: usize, out: *mut u8) -> c_int;
     pub fn bnp_decode_fq12_batch(input: *const u8, n: usize, f12: *mut u64, status: *mut u8) -> c_int;
+    /// scalar multiplication on the device (include/bnp.h): group 1 = G1, 2 = G2; scalars [4][n] plain little-endian limbs
+    pub fn bnp_scalar_mul_batch(group: c_int, pts: *const u64, scalars: *const u64, out: *mut u64, inf: *mut u8, n: usize) -> c_int;
     pub fn bnp_eip197_pairing_check(input: *const u8, k: usize, result: *mut c_int) -> c_int;
     pub fn bnp_pairing_dev(device: c_int, stream: *mut c_void, g1: *const u64, g2: *const u64, out: *mut u64,
                            n: usize, k: c_int, variant: c_int) -> c_int;

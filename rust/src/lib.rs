@@ -16,8 +16,8 @@
 //! Errors: the reference panics (assert!/unwrap); these wrappers panic with libbnp's message.
 mod ffi;
 
-use ark_bn254::{Fq, Fq12, Fq2, G1Affine, G2Affine};
-use ark_ff::{BigInt, Fp};
+use ark_bn254::{Fq, Fq12, Fq2, Fr, G1Affine, G2Affine};
+use ark_ff::{BigInt, Fp, PrimeField};
 use plonky2_bn254::fields::native::MyFq12;
 use std::ffi::CStr;
 
@@ -91,6 +91,54 @@ fn pack_fq12(fs: &[MyFq12]) -> Vec<u64> {
 fn unpack_fq12(b: &[u64], n: usize) -> Vec<MyFq12> {
     (0..n)
         .map(|e| MyFq12 { coeffs: core::array::from_fn(|k| get(b, k, n, e)) })
+        .collect()
+}
+
+// ---- scalar multiplication ---------------------------------------------------
+fn pack_scalars(ks: &[Fr]) -> Vec<u64> {
+    let n = ks.len();
+    let mut b = vec![0u64; 4 * n];
+    for (e, k) in ks.iter().enumerate() {
+        let l = k.into_bigint().0; // the plain integer, not the Montgomery residue
+        for j in 0..4 {
+            b[j * n + e] = l[j];
+        }
+    }
+    b
+}
+
+/// `ps[i] * ks[i]` for the whole slice on the device - what `(G1Affine * Fr).into()` gives one at a time
+/// (miller_loop_native.rs:333); the identity comes back as `G1Affine::identity()`.
+pub fn g1_scalar_mul_batch(ps: &[G1Affine], ks: &[Fr]) -> Vec<G1Affine> {
+    assert_eq!(ps.len(), ks.len());
+    init();
+    let n = ps.len();
+    let (g1, sc) = (pack_g1(ps), pack_scalars(ks));
+    let mut out = vec![0u64; 8 * n];
+    let mut inf = vec![0u8; n];
+    check(unsafe { ffi::bnp_scalar_mul_batch(1, g1.as_ptr(), sc.as_ptr(), out.as_mut_ptr(), inf.as_mut_ptr(), n) });
+    (0..n)
+        .map(|e| if inf[e] != 0 { G1Affine::identity() } else { G1Affine::new_unchecked(get(&out, 0, n, e), get(&out, 1, n, e)) })
+        .collect()
+}
+
+/// `qs[i] * ks[i]` on G2 (miller_loop_native.rs:334)
+pub fn g2_scalar_mul_batch(qs: &[G2Affine], ks: &[Fr]) -> Vec<G2Affine> {
+    assert_eq!(qs.len(), ks.len());
+    init();
+    let n = qs.len();
+    let (g2, sc) = (pack_g2(qs), pack_scalars(ks));
+    let mut out = vec![0u64; 16 * n];
+    let mut inf = vec![0u8; n];
+    check(unsafe { ffi::bnp_scalar_mul_batch(2, g2.as_ptr(), sc.as_ptr(), out.as_mut_ptr(), inf.as_mut_ptr(), n) });
+    (0..n)
+        .map(|e| {
+            if inf[e] != 0 {
+                G2Affine::identity()
+            } else {
+                G2Affine::new_unchecked(Fq2::new(get(&out, 0, n, e), get(&out, 1, n, e)), Fq2::new(get(&out, 2, n, e), get(&out, 3, n, e)))
+            }
+        })
         .collect()
 }
 
