@@ -11,11 +11,14 @@ The split is automatic: `Builder.cut()` marks candidate boundaries; `split` pick
 algorithmic work, computes the values live across each boundary, gives each a state index (indices are reused
 once a value is dead) and adds the LDG / STG instructions.  Constants and program inputs are simply re-loaded.
 """
+import os
+
 from . import isa
 from .fuse import FOp
 
 REMAT = ("LDC", "LDG")
 COST = {"MUL": 336, "SQR": 272, "MULFP": 272, "INV": 60000}
+TAIL = "0.5,0.25,0.12"   # lengths of the last phases relative to the others
 
 
 def split(fops, n_phases):
@@ -29,12 +32,25 @@ def split(fops, n_phases):
         cum.append(acc)
         acc += COST.get(o.op, 20)
     total = acc
-    chosen = []
-    for k in range(1, n_phases):
-        target = total * k / n_phases
-        best = min(cuts, key=lambda i: abs(cum[i] - target))
-        if best not in chosen:
-            chosen.append(best)
+    # Relative lengths of the phases: equal, except that the LAST ones taper off (TAIL, overridden by BNP_PHASE_TAIL).
+    # Tasks are handed out phase by phase, so the warps that find the queue empty at the end of a launch wait for the
+    # last-phase tasks still running - half a task each on average.  With equal phases that was 3 % of a 2^16 launch
+    # (ncu: EXIT + barrier samples); a last phase of 1/80 of the program instead of 1/13 brings back 1.5 %
+    # (profiles/experiments_r2.txt, A/B on one box).
+    weights = [1.0] * n_phases
+    tail = [float(x) for x in os.environ.get("BNP_PHASE_TAIL", TAIL).split(",") if x]
+    if tail and 4 * len(tail) <= n_phases:   # a taper needs a body of equal phases in front of it
+        weights[-len(tail):] = tail
+    # boundary k goes to the candidate nearest its target, among those that leave enough candidates on either side for
+    # the other boundaries (the candidates thin out towards the end of a program, the targets of the taper do not)
+    chosen, lo = [], 0
+    if len(cuts) >= n_phases - 1:
+        for k in range(1, n_phases):
+            target = total * sum(weights[:k]) / sum(weights)
+            hi = len(cuts) - (n_phases - 1 - k)          # exclusive
+            j = min(range(lo, hi), key=lambda j: abs(cum[cuts[j]] - target))
+            chosen.append(cuts[j])
+            lo = j + 1
     chosen.sort()
     bounds = [0] + chosen + [len(fops)]
     segs = [[o for o in fops[bounds[k]:bounds[k + 1]] if o.op != "CUT"] for k in range(len(bounds) - 1)]

@@ -262,6 +262,8 @@ def _miller_core(b, n_pairs, track_scale, pairs=None):
                 g = b.fq12_mul_034(g, e0, e1, e3)
         first = False
         if naf[i] != 0:
+            if i < 8:
+                b.cut()   # finer candidates near the end: the last phases of a split program taper off (phases.py)
             for pr in pairs:
                 scale_chord(pr)
                 e0, e1, e3 = pr.add_q(naf[i])
@@ -273,6 +275,7 @@ def _miller_core(b, n_pairs, track_scale, pairs=None):
 
     # Frobenius endpoints (:176-187, :266-280)
     for pr in pairs:
+        b.cut()
         if track_scale:
             # the scale of the first chord is Z before it, of the second Z after it
             q1x = b.const(_C2) * pr.Qx.conj()
@@ -281,6 +284,7 @@ def _miller_core(b, n_pairs, track_scale, pairs=None):
             e0, e1, e3 = pr.add_step(q1x, q1y)
             exp_w += 2
             g = b.fq12_mul_034(g, e0, e1, e3)
+            b.cut()
             q2x = b.const(_C2) * q1x.conj()
             nq2y = -(b.const(_C3) * q1y.conj())
             scale_chord(pr)
@@ -300,7 +304,9 @@ def _miller_exact(b, n_pairs):
     # f_ref = g * w^exp_w / (S * xi^exp_xi);  w^exp_w = xi^(exp_w div 6) * w^(exp_w mod 6)
     order = P * P - 1
     k = c_pow(XI, (exp_w // 6 - exp_xi) % order)
+    b.cut()
     corr = S.inv() * b.const(k)
+    b.cut()
     g = b.fq12_rot(g, exp_w % 6)
     return b.fq12_mul_fq2(g, corr)
 
@@ -331,21 +337,32 @@ def _hard_part_ref(b, m, tap=None):
     tap("mx3", mx3)
     mx3p = b.fq12_frobenius(mx3, 1)
     # y1 = conj(m), y3 = conj(mxp), y4 = conj(mx * mx2p), y5 = conj(mx2), y6 = conj(mx3 * mx3p)
+    # (cut candidates between the steps of the vectorial chain: the LAST phase of a split program wants to be short,
+    # phases.py)
     y4c = b.fq12_mul(mx, mx2p)       # conj(y4)
+    b.cut()
     y6c = b.fq12_mul(mx3, mx3p)      # conj(y6)
+    b.cut()
     # T0 = y6^2 * y4 * y5 = conj(y6c^2 * y4c * mx2)
     T0c = b.fq12_cyclo_sqr(y6c)
     T0c = b.fq12_mul(T0c, y4c)
+    b.cut()
     T0c = b.fq12_mul(T0c, mx2)
+    b.cut()
     # T1 = y3 * y5 * T0 = conj(mxp * mx2 * T0c)
     T1c = b.fq12_mul(b.fq12_mul(mxp, mx2), T0c)
+    b.cut()
     # T0 = y2 * T0
     T0 = b.fq12_mul_conj(y2, T0c)
+    b.cut()
     T1 = b.fq12_conj(b.fq12_cyclo_sqr(T1c))   # T1^2
     T1 = b.fq12_mul(T1, T0)
+    b.cut()
     T1 = b.fq12_cyclo_sqr(T1)
     T0 = b.fq12_mul_conj(T1, m)               # T1 * y1
+    b.cut()
     T1 = b.fq12_mul(T1, y0)
+    b.cut()
     T0 = b.fq12_cyclo_sqr(T0)
     return b.fq12_mul(T0, T1)
 
@@ -364,14 +381,20 @@ def _hard_part_ark(b, e):
     y6c_old = b.fq12_pow_x_cyclo(y5)           # y5^x = conj(y6_old)  => final y6 = conj(y6_old) = y5^x
     y6 = y6c_old
     y7 = b.fq12_mul(y6, y4)
+    b.cut()
     y8 = b.fq12_mul(y7, y3)
+    b.cut()
     y9 = b.fq12_mul_conj(y8, y1c)              # y8 * y1
     y10 = b.fq12_mul(y8, y4)
+    b.cut()
     y11 = b.fq12_mul(y10, e)
     y12 = b.fq12_frobenius(y9, 1)
+    b.cut()
     y13 = b.fq12_mul(y12, y11)
     y8f = b.fq12_frobenius(y8, 2)
+    b.cut()
     y14 = b.fq12_mul(y8f, y13)
+    b.cut()
     y15 = b.fq12_frobenius(b.fq12_mul_conj(y9, e), 3)
     return b.fq12_mul(y15, y14)
 

@@ -209,6 +209,21 @@ def test_phase_split_programs_equal_the_monolithic_program(name, k):
     assert max(works) < 1.25 * sum(works) / k  # balanced: the longest phase bounds the partial last round
 
 
+def test_split_phases_taper_off():
+    """the shipped split: 16 phases, the last three about 1/2, 1/4 and 1/8 of the others (phases.TAIL) - the warps
+    that run out of tasks at the end of a launch wait for half a LAST-phase task on average"""
+    from plonky2_bn254_pairing_b200.microcode import fuse, phases
+
+    for name in ("pairing_v0", "pairing_v1", "final_exp_v0", "pairing_x4_v0"):
+        fops = fuse.fuse(programs.build_program(name, ConstPool()).ops)
+        segs, _ = phases.split(fops, 16)
+        assert len(segs) == 16
+        w = [sum(phases.COST.get(o.op, 20) for o in seg) for seg in segs]
+        body = sum(w[:13]) / 13
+        assert max(w[:13]) < 1.25 * body
+        assert 0.35 * body < w[13] < 0.65 * body and 0.15 * body < w[14] < 0.35 * body and w[15] < 0.2 * body, (name, w)
+
+
 def test_validation_programs():
     """SURVEY 8(f).4: the residuals are all zero exactly for points `G1Affine::new` / `G2Affine::new` accept."""
     p, q = PTS[0]
