@@ -467,16 +467,20 @@ def run_extras(rig, peak, args):
         pts1, pts2 = api.unpack_soa(g1w[:, :, :256]), api.unpack_soa(g2w[:, :, :256])
         b1 = b"".join(W.encode_g1((r[0], r[1]), W.COMPRESSED) for r in pts1) * (nw // 256)
         b2 = b"".join(W.encode_g2(((r[0], r[1]), (r[2], r[3])), W.COMPRESSED) for r in pts2) * (nw // 256)
-        api.decode_g1_soa(W.COMPRESSED, b1[:32 * 256])
-        t0 = _time.perf_counter()
-        d1, s1 = api.decode_g1_soa(W.COMPRESSED, b1)
-        t1 = _time.perf_counter()
-        d2, s2 = api.decode_g2_soa(W.COMPRESSED, b2, check_subgroup=True)
-        t2 = _time.perf_counter()
+        # steady state: the first full-size call of each kind pays for the library's buffers (cudaMalloc after torch
+        # has just released gigabytes is slow and erratic: 10 ms ... 1 s), the second is timed
+        for rep in range(2):
+            t0 = _time.perf_counter()
+            d1, s1 = api.decode_g1_soa(W.COMPRESSED, b1)
+            t1 = _time.perf_counter()
+        for rep in range(2):
+            t1b = _time.perf_counter()
+            d2, s2 = api.decode_g2_soa(W.COMPRESSED, b2, check_subgroup=True)
+            t2 = _time.perf_counter()
         okw = (not s1.any() and not s2.any() and np.array_equal(d1[:, :, :256], g1w[:, :, :256])
                and np.array_equal(d2[:, :, :256], g2w[:, :, :256]) and np.array_equal(d2[:, :, -256:], g2w[:, :, :256]))
         extra["wire_decode_2e16"] = {
-            "g1_compressed_points_per_s": nw / (t1 - t0), "g2_compressed_with_subgroup_check_points_per_s": nw / (t2 - t1),
+            "g1_compressed_points_per_s": nw / (t1 - t0), "g2_compressed_with_subgroup_check_points_per_s": nw / (t2 - t1b),
             "api": "bnp_decode_g1_batch / bnp_decode_g2_batch (host pointers, copies and status bytes included)",
             "equal_to_the_encoded_points": bool(okw)}
     if not rig.all_ok(bool(okw)):
@@ -493,18 +497,20 @@ def run_extras(rig, peak, args):
         rng = np.random.default_rng(0xB2540F05)
         ks = rng.integers(0, 1 << 63, size=(4, ns), dtype=np.uint64)
         ks[3] &= np.uint64((1 << 61) - 1)   # below r: the scalars a verifier draws
-        api.scalar_mul_soa(1, np.ascontiguousarray(g1s[:, :, :256]), np.ascontiguousarray(ks[:, :256]))
-        t0 = _time.perf_counter()
-        kp, i1 = api.scalar_mul_soa(1, g1s, ks)
-        t1 = _time.perf_counter()
-        kq, i2 = api.scalar_mul_soa(2, g2s, ks)
-        t2 = _time.perf_counter()
+        for rep in range(2):   # the second call of each kind is timed (see the wire formats above)
+            t0 = _time.perf_counter()
+            kp, i1 = api.scalar_mul_soa(1, g1s, ks)
+            t1 = _time.perf_counter()
+        for rep in range(2):
+            t1b = _time.perf_counter()
+            kq, i2 = api.scalar_mul_soa(2, g2s, ks)
+            t2 = _time.perf_counter()
         m = 512
         a = api.pairing_soa(np.ascontiguousarray(kp[:, :, :m]), np.ascontiguousarray(g2s[:, :, :m]))
         b = api.pairing_soa(np.ascontiguousarray(g1s[:, :, :m]), np.ascontiguousarray(kq[:, :, :m]))
         oks = bool(not i1.any() and not i2.any() and np.array_equal(a, b))
         extra["scalar_mul_2e16"] = {
-            "g1_points_per_s": ns / (t1 - t0), "g2_points_per_s": ns / (t2 - t1),
+            "g1_points_per_s": ns / (t1 - t0), "g2_points_per_s": ns / (t2 - t1b),
             "api": "bnp_scalar_mul_batch (host pointers, copies included), 254-bit scalars, one thread per point",
             "pairing_commutes_on_512_sampled": oks}
     if not rig.all_ok(bool(oks)):
