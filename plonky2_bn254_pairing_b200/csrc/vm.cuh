@@ -61,9 +61,6 @@ __device__ __constant__ u32 BNP_CONSTS[BNP_MAX_CONST][16];
 #ifndef BNP_UNIFORM_DECODE
 #define BNP_UNIFORM_DECODE 1
 #endif
-#ifndef BNP_LIN_PREFETCH
-#define BNP_LIN_PREFETCH 0
-#endif
 #ifndef BNP_ST_WAIT_LATE
 #define BNP_ST_WAIT_LATE 0
 #endif
@@ -176,9 +173,9 @@ __device__ __forceinline__ void stg_fp(u64* arr, u32 f, u32 n, u32 e, const u32*
 #else
 #define BNP_UNI(x) (x)
 #endif
-#define BNP_LIN_FETCH(J, ZA, ZB, TT)                                          \
+#define BNP_LIN_FETCH(PE, ZA, ZB, TT)                                         \
     {                                                                         \
-        TT = BNP_UNI(__ldg(ents + (J)));                                      \
+        TT = BNP_UNI(__ldg(PE));                                              \
         S.issue_fq(ZA, TT & 0x1ffu);                                          \
         S.issue_fq(ZB, (TT >> 16) & 0x1ffu);                                  \
         S.wait_half(ZA);                                                      \
@@ -239,29 +236,12 @@ __device__ __forceinline__ void vm_lin(const Slots<T>& S, Fp2& out, u32 n, const
     u64 E0[5], O0[5], E1[5], O1[5];
 #pragma unroll
     for (int i = 0; i < 5; i++) E0[i] = O0[i] = E1[i] = O1[i] = 0ull;
-#if BNP_LIN_PREFETCH
-    // the entry word of pair j + 1 is fetched while pair j is accumulated (the list is followed by at least one more
-    // program word, so reading one word past it is safe)
-    u32 tn = __ldg(ents);
-#pragma unroll 1
-    for (u32 j = 0; j < n; j++) {
-        u32 za[8], zb[8];
-        const u32 ta = tn;
-        tn = __ldg(ents + j + 1u);
-        S.issue_half(za, ta & 0xffu, (ta >> 8) & 1u);
-        S.issue_half(zb, (ta >> 16) & 0xffu, (ta >> 24) & 1u);
-        S.wait_half(za);
-        S.dep_half(zb);
-        BNP_LIN_ACC(za, zb, ta);
-    }
-#else
 #pragma unroll 1
     for (u32 j = 0; j < n; j++) {
         u32 za[8], zb[8], ta;
-        BNP_LIN_FETCH(j, za, zb, ta);
+        BNP_LIN_FETCH(ents + j, za, zb, ta);
         BNP_LIN_ACC(za, zb, ta);
     }
-#endif
     u32 v0[9], v1[9];
     lin_merge(v0, E0, O0);
     lin_merge(v1, E1, O1);
