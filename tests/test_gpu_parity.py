@@ -267,10 +267,18 @@ def test_all_devices_in_one_process(lib):
         g2 = np.ascontiguousarray(api.pack_soa(api.g2_rows(Qs))[:, :, (idx * 3 + idx // 32) % 32])
         got = api.pairing_soa(g1, g2)
         prod = api.pairing_product_soa(g1, g2)
+        ks = api._scalar_rows(O.seeded_scalars(0xB2540F06, n))
+        kp_multi, kq_multi = api.scalar_mul_soa(1, g1, ks), api.scalar_mul_soa(2, g2, ks)
+        ok_multi = api.validate_soa(g1, g2)
     finally:
         lib.bnp_shutdown()
         native.init([0])
     assert np.array_equal(prod, api.pairing_product_soa(g1, g2))
+    # the index-range split of the other host-pointer entries: the same bits as one device
+    kp_one, kq_one = api.scalar_mul_soa(1, g1, ks), api.scalar_mul_soa(2, g2, ks)
+    assert np.array_equal(kp_multi[0], kp_one[0]) and np.array_equal(kp_multi[1], kp_one[1])
+    assert np.array_equal(kq_multi[0], kq_one[0]) and np.array_equal(kq_multi[1], kq_one[1])
+    assert ok_multi.all() and np.array_equal(got, api.pairing_soa(g1, g2))
     acc = np.ascontiguousarray(got[:, :, :1])
     for i in range(1, 64):
         acc = api.fq12_mul_soa(acc, np.ascontiguousarray(got[:, :, i:i + 1]))
