@@ -99,3 +99,27 @@ fn wire_formats_match_ark_serialize() {
         assert_eq!(&bytes[384 * i..384 * (i + 1)], &want[..]);
     }
 }
+
+/// scalar multiplication on the device against ark-ec's (`(P * k).into()`, the expression the reference's
+/// own tests build their points with, miller_loop_native.rs:331-334), the identity included.
+#[test]
+fn scalar_mul_matches_ark_ec() {
+    use ark_bn254::Fr;
+    use ark_ec::CurveGroup;
+    use ark_ff::{One, Zero};
+    let mut rng = ark_std::test_rng();
+    let n = 64;
+    let ps: Vec<G1Affine> = (0..n).map(|_| G1Affine::rand(&mut rng)).collect();
+    let qs: Vec<G2Affine> = (0..n).map(|_| G2Affine::rand(&mut rng)).collect();
+    let mut ks: Vec<Fr> = (0..n).map(|_| Fr::rand(&mut rng)).collect();
+    ks[0] = Fr::zero();
+    ks[1] = Fr::one();
+    ks[2] = -Fr::one();
+    let g1 = gpu::g1_scalar_mul_batch(&ps, &ks);
+    let g2 = gpu::g2_scalar_mul_batch(&qs, &ks);
+    for i in 0..n {
+        assert_eq!(g1[i], (ps[i] * ks[i]).into_affine());
+        assert_eq!(g2[i], (qs[i] * ks[i]).into_affine());
+    }
+    assert!(g1[0].is_zero() && g2[0].is_zero());
+}
