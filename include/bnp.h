@@ -95,7 +95,7 @@ int bnp_pow_u64_batch(const uint64_t* in, uint64_t* out, size_t n, const uint64_
 int bnp_validate_batch(const uint64_t* g1 /* [2][4][n] */, const uint64_t* g2 /* [4][4][n] */, unsigned char* ok /* [n] */, size_t n);
 /* Scalar multiplication on the device: out[e] = scalars[e] * pts[e] on G1 (group = 1, pts and out
  * [2][4][n]) or G2 (group = 2, [4][4][n]) - what `G1Affine * Fr` / `G2Affine * Fr` compute in the reference's tests
- * (miller_loop_native.rs:331-334) and what a verifier folding many pairing checks into one by a random linear
+ * (test_to_one, final_exp_native.rs:245-250) and what a verifier folding many pairing checks into one by a random linear
  * combination needs in front of the pairing batch.  scalars: [4][n], each a PLAIN 256-bit integer in four little-endian
  * 64-bit limbs (ark's `Fr::into_bigint()`), any value below 2^256.  inf[e] = 1 where the result is the point at
  * infinity (its coordinates come back as (0, 0), ark's encoding); input coordinates (0, 0) are the point at infinity.

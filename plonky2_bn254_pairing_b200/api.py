@@ -359,7 +359,7 @@ def _scalar_rows(ks):
 
 
 def g1_scalar_mul_batch(Ps, ks):
-    """[k_i * P_i] on G1 - `G1Affine * Fr` of the reference's tests (miller_loop_native.rs:333), batched.  Points are
+    """[k_i * P_i] on G1 - `G1.mul(s).into()` of the reference's test_to_one (final_exp_native.rs:247), batched.  Points are
     (x, y) integer pairs; the point at infinity is None (in and out)."""
     if not Ps:
         return []
@@ -369,7 +369,7 @@ def g1_scalar_mul_batch(Ps, ks):
 
 
 def g2_scalar_mul_batch(Qs, ks):
-    """[k_i * Q_i] on G2 (`G2Affine * Fr`, miller_loop_native.rs:334); points are ((x0, x1), (y0, y1)) or None."""
+    """[k_i * Q_i] on G2 (`G2.mul(t).into()`, final_exp_native.rs:248); points are ((x0, x1), (y0, y1)) or None."""
     if not Qs:
         return []
     zero = ((0, 0), (0, 0))

@@ -6,7 +6,7 @@
 // the bits of a per-element scalar, which the grid-uniform sequencer cannot do).  Jacobian coordinates on
 // y^2 = x^3 + b (a = 0), Z = 0 for the point at infinity; left-to-right binary method, one doubling per bit and one
 // mixed addition (the base point stays affine) per set bit.  The reference gets the same values from ark-ec
-// (`G1Affine * Fr`, `G2Affine * Fr`: miller_loop_native.rs:331-334 draws its test points that way); the group law is
+// (`G1.mul(s).into()`, `G2.mul(t).into()`: final_exp_native.rs:245-250 builds its test points that way); the group law is
 // exact, so any correct schedule gives the same affine result.  Exceptional cases of the addition (accumulator at
 // infinity, equal to +-P) are handled per thread: they cannot occur for scalars below r on points of order r, but the
 // entry accepts every 256-bit scalar and every on-curve point.

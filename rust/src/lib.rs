@@ -108,7 +108,7 @@ fn pack_scalars(ks: &[Fr]) -> Vec<u64> {
 }
 
 /// `ps[i] * ks[i]` for the whole slice on the device - what `(G1Affine * Fr).into()` gives one at a time
-/// (miller_loop_native.rs:333); the identity comes back as `G1Affine::identity()`.
+/// (`G1.mul(s).into()`, final_exp_native.rs:247); the identity comes back as `G1Affine::identity()`.
 pub fn g1_scalar_mul_batch(ps: &[G1Affine], ks: &[Fr]) -> Vec<G1Affine> {
     assert_eq!(ps.len(), ks.len());
     init();
@@ -122,7 +122,7 @@ pub fn g1_scalar_mul_batch(ps: &[G1Affine], ks: &[Fr]) -> Vec<G1Affine> {
         .collect()
 }
 
-/// `qs[i] * ks[i]` on G2 (miller_loop_native.rs:334)
+/// `qs[i] * ks[i]` on G2 (`G2.mul(t).into()`, final_exp_native.rs:248)
 pub fn g2_scalar_mul_batch(qs: &[G2Affine], ks: &[Fr]) -> Vec<G2Affine> {
     assert_eq!(qs.len(), ks.len());
     init();

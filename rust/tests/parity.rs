@@ -101,7 +101,7 @@ fn wire_formats_match_ark_serialize() {
 }
 
 /// scalar multiplication on the device against ark-ec's (`(P * k).into()`, the expression the reference's
-/// own tests build their points with, miller_loop_native.rs:331-334), the identity included.
+/// test_to_one builds its points with, final_exp_native.rs:245-250), the identity included.
 #[test]
 fn scalar_mul_matches_ark_ec() {
     use ark_bn254::Fr;

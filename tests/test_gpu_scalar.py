@@ -1,5 +1,5 @@
 """Scalar multiplication on the device (csrc/scalar.cuh): `G1Affine * Fr` / `G2Affine * Fr` of the reference's
-tests (miller_loop_native.rs:331-334), against the oracle's affine double-and-add and, at size, through the pairing:
+test_to_one (`G1.mul(s).into()`, `G2.mul(t).into()`: final_exp_native.rs:245-250), against the oracle's affine double-and-add and, at size, through the pairing:
 e(k P, Q) == e(P, k Q)."""
 import numpy as np
 import pytest
@@ -70,3 +70,21 @@ def test_scalar_mul_commutes_with_the_pairing_at_size(lib):
     # and one of them against the oracle end to end
     k0 = sum(int(ks[j, 17]) << (64 * j) for j in range(4))
     assert api.unpack_soa(a[:, :, 17:18])[0] == O.pairing(O.g1_mul(Ps[17], k0), Qs[(7 * 17) % 64])
+
+
+def test_to_one_with_points_made_on_the_device(lib):
+    """the reference's test_to_one (final_exp_native.rs:241-263) with `G1.mul(s).into()` / `G2.mul(t).into()` done by the
+    device: P0 = s G1, Q0 = t G2, P1 = s t G1, Q1 = -G2  =>  e(P0, Q0) e(P1, Q1) = 1, and the multi Miller loop equals
+    the product of the single ones"""
+    s, t = 5, 6
+    P0, P1 = api.g1_scalar_mul_batch([O.G1_GEN, O.G1_GEN], [s, s * t])
+    (Q0,) = api.g2_scalar_mul_batch([O.G2_GEN], [t])
+    Q1 = O.g2_neg(O.G2_GEN)
+    assert (P0, P1, Q0) == (O.g1_mul(O.G1_GEN, s), O.g1_mul(O.G1_GEN, s * t), O.g2_mul(O.G2_GEN, t))
+    m = api.multi_miller_loop_native([(P0, Q0), (P1, Q1)])
+    m0, m1 = api.miller_loop_native(Q0, P0), api.miller_loop_native(Q1, P1)
+    assert m == api.fq12_mul_batch([m0], [m1])[0]
+    r_sep = api.fq12_mul_batch([api.final_exp_native(m0)], [api.final_exp_native(m1)])[0]
+    assert r_sep == api.final_exp_native(m)
+    one = [1] + [0] * 11
+    assert r_sep == one
