@@ -186,9 +186,10 @@ int launch_T(DevCtx& c, const BnpProgram& p, int pidx, cudaStream_t st, u64* con
     }
     const size_t n_chunks = (n + BNP_CHUNK - 1) / BNP_CHUNK;  // a warp works on 32 pairings, one per lane
     const size_t resident_warps = (size_t)per_sm * c.sm_count * (T / 32);
-    // Tasks are (phase, chunk) pairs of equal length handed out breadth-first, so a launch takes ceil(tasks / warps)
-    // task times: split when the unsplit batch would leave the last round badly filled, with the phase count whose
-    // last round is fullest (2^16 pairings on 148 x 12 warps: 13 phases make 14.99 rounds, 16 make 18.45 - 3 % idle).
+    // Tasks are (phase, chunk) pairs handed out breadth-first.  The last BNP_PHASE_TAPER phases of a split program are
+    // short (they bound the idle time at the end of the launch); the equal phases in front of them cost
+    // ceil(tasks / warps) task times, so the phase count is the one whose body fills its last round best (2^16 pairings
+    // on 148 x 12 warps: 13 body phases make 14.99 rounds).  Batches that fill their rounds unsplit are not split.
     bool split = false;
     int n_ph = 0;
     const int* ph_idx = nullptr;
@@ -197,7 +198,8 @@ int launch_T(DevCtx& c, const BnpProgram& p, int pidx, cudaStream_t st, u64* con
         const double loss1 = std::ceil(rounds) / rounds - 1.0;
         double best = 1e9;
         for (int K : var_K) {
-            const double lossK = std::ceil(rounds * K) / (rounds * K) - 1.0;
+            const double body = rounds * std::max(1, K - BNP_PHASE_TAPER);
+            const double lossK = std::ceil(body) / body - 1.0;
             if (lossK <= best) {   // ties: the finer split
                 best = lossK;
                 n_ph = K;

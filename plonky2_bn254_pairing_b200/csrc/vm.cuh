@@ -24,7 +24,9 @@
 
 #define BNP_NARR 6
 #define BNP_MAX_CONST 128
+#ifndef BNP_MAX_PHASES
 #define BNP_MAX_PHASES 16
+#endif
 #define BNP_CHUNK 32  // pairings per warp-task
 
 struct VmArgs {
