@@ -48,6 +48,10 @@ extern "C" {
 int bnp_init(const int* devices, int n_devices);
 void bnp_shutdown(void);
 int bnp_device_count(void); /* devices initialised by bnp_init */
+/* How bnp_pairing_product moves the per-device partial products (384 bytes each) in a multi-device context: "nccl" (one
+ * ncclAllGather over the communicators bnp_init created; libnccl is loaded at run time) or "peer-copy" (NCCL absent,
+ * failed, or a single device). */
+const char* bnp_gather_transport(void);
 const char* bnp_strerror(int code);
 const char* bnp_last_error(void); /* detail of the last BNP_ECUDA on this thread */
 

@@ -1,6 +1,7 @@
 // libbnp.so runtime: C ABI of include/bnp.h on top of the sequencer kernel (vm.cuh).
 // No torch types, no CPU fallback: every compute entry point fails with BNP_ENODEV without a device.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -629,6 +630,66 @@ int wire_decode_host(int group, int fmt, const uint8_t* in, size_t n, uint64_t* 
 
 extern "C" {
 
+// ---- NCCL, loaded at run time (no link-time dependency: the library must load on a box without it) ----
+// The single-process multi-device path has ONE exchange step: the all-gather of one 384-byte partial Fq12 product per
+// device in bnp_pairing_product.  bnp_init with several devices creates one communicator per device
+// (ncclCommInitAll); if NCCL is missing or fails, the gather falls back to peer copies (bnp_gather_transport says which).
+struct NcclApi {
+    void* h = nullptr;
+    int (*CommInitAll)(void**, int, const int*) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    std::vector<void*> comms;     // one per g_ctx entry, in order
+    std::vector<u64*> recv;       // per device: [ndev][48] u64
+    bool ok = false;
+};
+NcclApi g_nccl;
+const int BNP_NCCL_UINT64 = 5;    // ncclUint64 (nccl.h: ncclInt8 0, ncclUint8 1, ncclInt32 2, ncclUint32 3, ncclInt64 4, ncclUint64 5)
+
+void nccl_teardown() {
+    if (g_nccl.ok)
+        for (size_t d = 0; d < g_nccl.comms.size(); d++)
+            if (g_nccl.comms[d]) g_nccl.CommDestroy(g_nccl.comms[d]);
+    for (size_t d = 0; d < g_nccl.recv.size(); d++)
+        if (g_nccl.recv[d] && d < g_ctx.size() && cudaSetDevice(g_ctx[d].dev) == cudaSuccess) cudaFree(g_nccl.recv[d]);
+    g_nccl.comms.clear();
+    g_nccl.recv.clear();
+    g_nccl.ok = false;
+}
+
+void nccl_setup() {
+    nccl_teardown();
+    if (g_ctx.size() < 2 || getenv("BNP_NO_NCCL")) return;
+    if (!g_nccl.h) {
+        for (const char* name : {"libnccl.so.2", "libnccl.so"})
+            if ((g_nccl.h = dlopen(name, RTLD_NOW | RTLD_GLOBAL))) break;
+        if (!g_nccl.h) return;
+        g_nccl.CommInitAll = (int (*)(void**, int, const int*))dlsym(g_nccl.h, "ncclCommInitAll");
+        g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.h, "ncclCommDestroy");
+        g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(g_nccl.h, "ncclAllGather");
+        g_nccl.GroupStart = (int (*)())dlsym(g_nccl.h, "ncclGroupStart");
+        g_nccl.GroupEnd = (int (*)())dlsym(g_nccl.h, "ncclGroupEnd");
+    }
+    if (!g_nccl.CommInitAll || !g_nccl.CommDestroy || !g_nccl.AllGather || !g_nccl.GroupStart || !g_nccl.GroupEnd) return;
+    std::vector<int> devs;
+    for (auto& c : g_ctx) devs.push_back(c.dev);
+    g_nccl.comms.assign(g_ctx.size(), nullptr);
+    if (g_nccl.CommInitAll(g_nccl.comms.data(), (int)devs.size(), devs.data()) != 0) {
+        g_nccl.comms.clear();
+        return;
+    }
+    g_nccl.recv.assign(g_ctx.size(), nullptr);
+    for (size_t d = 0; d < g_ctx.size(); d++)
+        if (cudaSetDevice(g_ctx[d].dev) != cudaSuccess || cudaMalloc(&g_nccl.recv[d], 384 * g_ctx.size()) != cudaSuccess) {
+            g_nccl.ok = true;  // so that teardown destroys the communicators
+            nccl_teardown();
+            return;
+        }
+    g_nccl.ok = true;
+}
+
 int bnp_init(const int* devices, int n_devices) {
     std::lock_guard<std::mutex> lk(g_mu);
     int count = 0;
@@ -648,11 +709,15 @@ int bnp_init(const int* devices, int n_devices) {
         int rc = init_device(devices[i]);
         if (rc) return rc;
     }
+    if (g_ctx.size() >= 2 && g_nccl.comms.size() != g_ctx.size()) nccl_setup();
     return BNP_OK;
 }
 
+const char* bnp_gather_transport(void) { return g_nccl.ok ? "nccl" : "peer-copy"; }
+
 void bnp_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
+    nccl_teardown();
     for (auto& c : g_ctx) {
         if (cudaSetDevice(c.dev) != cudaSuccess) continue;
         cudaStreamSynchronize(c.stream);
@@ -850,9 +915,31 @@ int bnp_pairing_product(const uint64_t* g1, const uint64_t* g2, uint64_t* out, s
     }
     // gather: 48 u64 rows of one element each, into column `slot` of c0.stage[4] ([48][nparts])
     if ((rc = sync_all())) return rc;
+    bool gathered = false;
+    if (g_nccl.ok && nparts == g_ctx.size()) {
+        // the exchange step as ONE NCCL all-gather of 384 bytes per device over NVLink (every device receives all
+        // partials; device 0 goes on), then the [rank][48] receive buffer is laid out as the [48][nparts] columns
+        bool fine = g_nccl.GroupStart() == 0;
+        for (size_t d = 0; fine && d < g_ctx.size(); d++) {
+            fine = cudaSetDevice(g_ctx[d].dev) == cudaSuccess &&
+                   g_nccl.AllGather(partial[d], g_nccl.recv[d], 48, BNP_NCCL_UINT64, g_nccl.comms[d], g_ctx[d].stream) == 0;
+        }
+        fine = (g_nccl.GroupEnd() == 0) && fine;
+        if (fine) {
+            CK(cudaSetDevice(c0.dev));
+            for (size_t r = 0; r < nparts; r++)
+                CK(cudaMemcpy2DAsync(c0.stage[4] + r, nparts * 8, g_nccl.recv[0] + 48 * r, 8, 8, 48, cudaMemcpyDeviceToDevice,
+                                     c0.stream));
+            if ((rc = sync_all())) return rc;
+            gathered = true;
+        } else {
+            sync_all();
+            g_nccl.ok = false;  // fall back to peer copies from now on
+        }
+    }
     slot = 0;
     CK(cudaSetDevice(c0.dev));
-    for (size_t d = 0; d < g_ctx.size(); d++) {
+    for (size_t d = 0; !gathered && d < g_ctx.size(); d++) {
         if (!partial[d]) continue;
         // peer copy over NVLink (falls back to staging through the host inside the driver if P2P is off)
         if (g_ctx[d].dev == c0.dev) {

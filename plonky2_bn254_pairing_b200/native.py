@@ -46,6 +46,7 @@ SIGNATURES = {
     "bnp_program_macs": (ctypes.c_uint64, [ctypes.c_char_p]),
     "bnp_program_macs_executed": (ctypes.c_uint64, [ctypes.c_char_p]),
     "bnp_launch_count": (ctypes.c_uint64, []),
+    "bnp_gather_transport": (ctypes.c_char_p, []),
     "bnp_imad_peak": (_int, [_int, ctypes.POINTER(ctypes.c_double)]),
     "bnp_imad32_peak": (_int, [_int, ctypes.POINTER(ctypes.c_double)]),
     "bnp_run_program_dev": (_int, [_int, ctypes.c_void_p, ctypes.c_char_p, _u64p, _u64p, _u64p, _u64p, _u64p, _sz]),

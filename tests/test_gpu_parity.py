@@ -267,6 +267,7 @@ def test_all_devices_in_one_process(lib):
         g2 = np.ascontiguousarray(api.pack_soa(api.g2_rows(Qs))[:, :, (idx * 3 + idx // 32) % 32])
         got = api.pairing_soa(g1, g2)
         prod = api.pairing_product_soa(g1, g2)
+        assert lib.bnp_gather_transport() in (b"nccl", b"peer-copy")
         ks = api._scalar_rows(O.seeded_scalars(0xB2540F06, n))
         kp_multi, kq_multi = api.scalar_mul_soa(1, g1, ks), api.scalar_mul_soa(2, g2, ks)
         ok_multi = api.validate_soa(g1, g2)

@@ -47,7 +47,18 @@ def single_process():
     for i in range(1, 257):
         acc = api.fq12_mul_soa(acc, np.ascontiguousarray(singles[:, :, i:i + 1]))
     assert np.array_equal(prod, acc), "global product over %d devices differs from the product of single pairings" % ndev
-    print("single-process, %d device(s): sharded batch and global product bit-exact" % ndev)
+    transport = native.lib().bnp_gather_transport().decode()
+    print("single-process, %d device(s): sharded batch and global product bit-exact (partials gathered by %s)" % (ndev, transport))
+    if ndev > 1 and transport == "nccl":
+        # the same product with NCCL switched off must give the same bits
+        native.lib().bnp_shutdown()
+        os.environ["BNP_NO_NCCL"] = "1"
+        native.init(list(range(ndev)))
+        assert native.lib().bnp_gather_transport() == b"peer-copy"
+        again = api.pairing_product_soa(np.ascontiguousarray(g1[:, :, :257]), np.ascontiguousarray(g2[:, :, :257]))
+        assert np.array_equal(prod, again)
+        del os.environ["BNP_NO_NCCL"]
+        print("  peer-copy gather: the same bits")
 
 
 def distributed():
