@@ -937,22 +937,23 @@ int bnp_pairing_product(const uint64_t* g1, const uint64_t* g2, uint64_t* out, s
             g_nccl.ok = false;  // fall back to peer copies from now on
         }
     }
-    slot = 0;
-    CK(cudaSetDevice(c0.dev));
-    for (size_t d = 0; !gathered && d < g_ctx.size(); d++) {
-        if (!partial[d]) continue;
-        // peer copy over NVLink (falls back to staging through the host inside the driver if P2P is off)
-        if (g_ctx[d].dev == c0.dev) {
-            CK(cudaMemcpy2DAsync(c0.stage[4] + slot, nparts * 8, partial[d], 8, 8, 48, cudaMemcpyDeviceToDevice, c0.stream));
-        } else {
-            // c0.stage[2] doubles as the bounce buffer and as device 0's own partial: the asynchronous copy that
-            // reads it above must have finished before a peer copy overwrites it
-            CK(cudaStreamSynchronize(c0.stream));
-            CK(cudaMemcpyPeer(c0.stage[2], c0.dev, partial[d], g_ctx[d].dev, 384));
-            CK(cudaMemcpy2DAsync(c0.stage[4] + slot, nparts * 8, c0.stage[2], 8, 8, 48, cudaMemcpyDeviceToDevice, c0.stream));
-            CK(cudaStreamSynchronize(c0.stream));
+    if (!gathered) {
+        // fallback: stream-ordered peer copies over NVLink into a [nparts][48] bounce buffer on device 0 (staged through
+        // the host inside the driver if P2P is off), then the same re-layout.  Everything is on c0.stream: a plain
+        // cudaMemcpyPeer runs on the legacy stream, which a non-blocking stream does not wait for (that race showed up
+        // with 8 devices).
+        CK(cudaSetDevice(c0.dev));
+        if ((rc = ensure_stage(c0, 5, 384 * nparts))) return rc;
+        slot = 0;
+        for (size_t d = 0; d < g_ctx.size(); d++) {
+            if (!partial[d]) continue;
+            CK(cudaMemcpyPeerAsync(c0.stage[5] + 48 * slot, c0.dev, partial[d], g_ctx[d].dev, 384, c0.stream));
+            slot++;
         }
-        slot++;
+        for (size_t r = 0; r < nparts; r++)
+            CK(cudaMemcpy2DAsync(c0.stage[4] + r, nparts * 8, c0.stage[5] + 48 * r, 8, 8, 48, cudaMemcpyDeviceToDevice,
+                                 c0.stream));
+        CK(cudaStreamSynchronize(c0.stream));
     }
     if ((rc = ensure_stage(c0, 3, 384))) return rc;
     if ((rc = ensure_stage(c0, 2, 384))) return rc;
