@@ -303,6 +303,9 @@ int init_device(int dev) {
         CK(cudaMalloc(&c.d_prog[i], bytes));
         CK(cudaMemcpy(c.d_prog[i], BNP_PROGRAMS[i].code, bytes, cudaMemcpyHostToDevice));
     }
+    // the uploads above come from pageable memory and run on the legacy stream, which the library's non-blocking streams
+    // do not wait for: make them complete before the first launch can be queued
+    CK(cudaDeviceSynchronize());
     g_ctx.push_back(c);
     return BNP_OK;
 }
