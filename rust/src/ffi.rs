@@ -15,6 +15,8 @@ pub const BNP_PREP_FQ: usize = 546;
 extern "C" {
     pub fn bnp_init(devices: *const c_int, n_devices: c_int) -> c_int;
     pub fn bnp_shutdown();
+    /// "nccl" or "peer-copy": how bnp_pairing_product gathers the per-device partials of a multi-device context
+    pub fn bnp_gather_transport() -> *const c_char;
     pub fn bnp_strerror(code: c_int) -> *const c_char;
     pub fn bnp_last_error() -> *const c_char;
     pub fn bnp_miller_loop_batch(g1: *const u64, g2: *const u64, out: *mut u64, n: usize) -> c_int;
