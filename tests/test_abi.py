@@ -75,3 +75,23 @@ def test_soa_layout_is_ark_montgomery_limbs():
 def test_myfq12_to_ark_order():
     x = list(range(12))
     assert api.myfq12_to_ark(x) == O.myfq12_to_ark(x)
+
+
+def test_scalar_limbs_and_window_digits():
+    """host side of bnp_scalar_mul_batch: scalars travel as four plain little-endian 64-bit limbs, SoA; and the signed
+    4-bit window recoding csrc/scalar.cuh performs per thread (restated here) represents every 256-bit scalar with
+    digits in [-8, 8) plus a carry digit, so the table P .. 8P suffices"""
+    ks = [0, 1, 7, 8, 15, 16, O.R_ORDER - 1, O.R_ORDER, (1 << 256) - 1, 1 << 255, 0x8888888888888888, 0x7777777777777777 << 64]
+    rows = api._scalar_rows(ks)
+    assert rows.shape == (4, len(ks)) and rows.dtype == np.uint64
+    for i, k in enumerate(ks):
+        assert sum(int(rows[j, i]) << (64 * j) for j in range(4)) == k
+        limbs = [int(rows[j, i]) for j in range(4)]
+        d, carry = [], 0
+        for n in range(64):
+            v = ((limbs[n >> 4] >> ((n & 15) * 4)) & 15) + carry
+            carry = 1 if v >= 8 else 0
+            d.append(v - (carry << 4))
+        d.append(carry)
+        assert all(-8 <= x <= 7 for x in d[:64]) and d[64] in (0, 1)
+        assert sum(x << (4 * n) for n, x in enumerate(d)) == k
